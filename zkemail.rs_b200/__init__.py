@@ -1,0 +1,6 @@
+"""zkemail.rs_b200 — B200-native batched DKIM e-mail verification (the hot path of
+zkemail_core::verify_email / verify_email_with_regex).  See DESIGN.md."""
+from .structs import (  # noqa: F401
+    DFA, CompiledRegex, Email, EmailVerifierOutput, EmailWithRegex, EmailWithRegexVerifierOutput,
+    ExternalInput, PublicKey, RegexConfig, RegexInfo, RegexPattern,
+)
