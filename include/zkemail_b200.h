@@ -1,0 +1,212 @@
+/*
+ * zkemail_b200.h — C ABI of libzkemail_b200.so: the B200-native batched replacement for the
+ * native execution of zkemail_core::verify_email / verify_email_with_regex.
+ *
+ * The reference has no FFI of its own: callers link the Rust crate and call
+ *     verify_email(&Email) -> EmailVerifierOutput                       core/src/circuits.rs:9
+ *     verify_email_with_regex(&EmailWithRegex) -> EmailWith..Output     core/src/circuits.rs:31
+ * so the entry points below are what a `zkemail-b200-sys` crate would bind (INTEGRATION.md shows
+ * the Rust side).  Plain pointers and sizes only; caller owns every input and output buffer; no
+ * function throws or aborts across the ABI: each returns a ZKB_E_* code (0 = ok), and every
+ * panic site of the reference becomes a per-email `status` (never a process abort).
+ *
+ * There is NO CPU fallback: every hash, modular exponentiation and DFA scan runs in sm_100a
+ * kernels.  If no CUDA device is usable, zkb_engine_create fails with ZKB_E_NO_DEVICE.
+ */
+#ifndef ZKEMAIL_B200_H
+#define ZKEMAIL_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKB_ABI_VERSION 1
+
+/* ---- library error codes (return values) ---- */
+enum {
+  ZKB_OK = 0,
+  ZKB_E_INVALID = 1,   /* bad argument */
+  ZKB_E_NO_DEVICE = 2, /* no usable CUDA device (there is no CPU fallback) */
+  ZKB_E_CUDA = 3,      /* CUDA runtime error (message on stderr) */
+  ZKB_E_NOMEM = 4,
+  ZKB_E_REGEX = 5,     /* pattern rejected by the regex compiler / bad table bytes */
+  ZKB_E_UNSUPPORTED = 6
+};
+
+/* ---- per-email status: one value per panic site of the reference, in program order ---- */
+enum {
+  ZKB_ST_OK = 0,
+  ZKB_ST_MAIL_PARSE = 1,    /* core/src/email.rs:26    parse_mail(..).unwrap()                   */
+  ZKB_ST_KEY = 2,           /* core/src/email.rs:28-29 DkimPublicKey::try_from_bytes(..).unwrap() */
+  ZKB_ST_DKIM_FAIL = 3,     /* core/src/circuits.rs:13 assert!(verified)                         */
+  ZKB_ST_NULL_EXTERNAL = 4, /* core/src/circuits.rs:24 expect("Value cannot be null") (wrappers)  */
+  ZKB_ST_CANONICALIZE = 5,  /* core/src/circuits.rs:35 canonicalize_signed_email(..).unwrap()     */
+  ZKB_ST_REGEX_HEADER = 6,  /* core/src/circuits.rs:45 assert!(verified)                         */
+  ZKB_ST_REGEX_BODY = 7,    /* core/src/circuits.rs:54 assert!(verified)                         */
+  ZKB_ST_BAD_DFA = 8,       /* core/src/regex.rs:32-33 DFA::from_bytes(..).unwrap()               */
+  ZKB_ST_UNSUPPORTED = 9    /* ed25519 key or rsa-sha1 signature: declined, never mis-verified   */
+};
+
+/* ---- DKIMResult detail (cfdkim DKIMError kind of the deciding signature) ---- */
+enum {
+  ZKB_DKIM_PASS = 0, ZKB_DKIM_NEUTRAL = 1, ZKB_DKIM_SYNTAX = 2, ZKB_DKIM_MISSING_TAG = 3,
+  ZKB_DKIM_VERSION = 4, ZKB_DKIM_DOMAIN_MISMATCH = 5, ZKB_DKIM_FROM_NOT_SIGNED = 6,
+  ZKB_DKIM_QUERY_METHOD = 7, ZKB_DKIM_EXPIRED = 8, ZKB_DKIM_CANON_TYPE = 9,
+  ZKB_DKIM_HASH_ALGO = 10, ZKB_DKIM_BODY_HASH = 11, ZKB_DKIM_SIG_SYNTAX = 12,
+  ZKB_DKIM_SIG_MISMATCH = 13, ZKB_DKIM_LENGTH_TAG = 14, ZKB_DKIM_ALGO_KEY_MISMATCH = 15
+};
+
+#define ZKB_MAX_PARTS 16
+
+/* Borrowed view of one `Email` (core/src/structs.rs:49-54).  external_inputs are pure host string
+ * glue (core/src/circuits.rs:18-27) and stay in the language wrapper. */
+typedef struct {
+  const char *from_domain;  size_t from_domain_len;
+  const uint8_t *raw_email; size_t raw_email_len;
+  const uint8_t *key;       size_t key_len;      /* PKCS#1 RSAPublicKey DER (PublicKey.key)   */
+  const char *key_type;     size_t key_type_len; /* "rsa" | "ed25519"    (PublicKey.key_type) */
+} zkb_email_view;
+
+/* Per-email result record (fixed size POD; identical layout to the oracle's zo_result). */
+typedef struct {
+  int32_t status;               /* ZKB_ST_* */
+  int32_t dkim_detail;          /* ZKB_DKIM_* */
+  uint8_t body_hash[32];        /* SHA-256 of the canonical body of the deciding signature   */
+  uint8_t header_hash[32];      /* SHA-256 of the signed-header preimage                     */
+  uint8_t from_domain_hash[32]; /* EmailVerifierOutput.from_domain_hash (circuits.rs:16)     */
+  uint8_t public_key_hash[32];  /* EmailVerifierOutput.public_key_hash  (circuits.rs:17)     */
+  uint8_t bh_ok, rsa_ok;
+  uint8_t pad[2];
+  uint32_t n_parts;             /* header parts then body parts, as far as evaluated */
+  struct {
+    uint32_t match_count, start, end; /* find_iter count and the first match span */
+    uint32_t captures_ok;             /* every expected capture is a substring of the match */
+  } parts[ZKB_MAX_PARTS];
+} zkb_result;
+
+/* One `CompiledRegex.verify_re` (core/src/structs.rs:16-27): forward + reverse dense DFA tables in
+ * the ZDF1 layout documented below.  Captures are per email and passed to zkb_verify_batch. */
+typedef struct {
+  const uint8_t *fwd; size_t fwd_len;
+  const uint8_t *bwd; size_t bwd_len;
+} zkb_dfa_view;
+
+/* Expected capture strings of one email: `CompiledRegex.captures` flattened over the parts of the
+ * regex set (header parts first).  part_has_captures[p]==0 means `captures: None` for part p. */
+typedef struct {
+  uint32_t part;       /* index into the regex set (header parts, then body parts) */
+  const char *s; size_t len;
+} zkb_capture;
+typedef struct {
+  const zkb_capture *caps; size_t n_caps;
+} zkb_email_captures;
+
+typedef struct {
+  int32_t device;        /* CUDA device ordinal */
+  int32_t host_threads;  /* 0 = all hardware threads */
+  int64_t now_unix;      /* clock for the x= tag check; 0 = wall clock (cfdkim behaviour) */
+  uint64_t chunk_emails; /* emails per pipeline chunk; 0 = default */
+  uint32_t flags;        /* reserved, 0 */
+  uint32_t rsa_lanes;    /* lanes cooperating on one signature (0 = default) */
+} zkb_options;
+
+typedef struct zkb_engine zkb_engine;
+typedef struct zkb_regex_set zkb_regex_set;
+typedef struct zkb_batch zkb_batch; /* a prepared batch resident in device memory */
+
+int zkb_abi_version(void);
+const char *zkb_strerror(int code);
+
+/* Engine = device context, streams, pinned staging, device arenas, key table. One per device. */
+int zkb_engine_create(const zkb_options *opt, zkb_engine **out);
+void zkb_engine_destroy(zkb_engine *e);
+
+/* Registers the DFAs of a RegexInfo (core/src/structs.rs:32-35): n_header header parts followed
+ * by n_body body parts.  header_present/body_present==0 model `None` (the part list is skipped,
+ * core/src/circuits.rs:39-56). Tables are validated (bad bytes => ZKB_E_REGEX, the per-email
+ * equivalent being ZKB_ST_BAD_DFA) and uploaded once. */
+int zkb_regex_set_create(zkb_engine *e, const zkb_dfa_view *parts, size_t n_header, size_t n_body,
+                         int header_present, int body_present, zkb_regex_set **out);
+void zkb_regex_set_destroy(zkb_regex_set *s);
+
+/* Batch entry point: verify_email (regex==NULL) or verify_email_with_regex over n emails.
+ * `captures` may be NULL (no capture checks) or point to n entries.  Synchronous; thread-safe
+ * for distinct engines, serialised per engine.  Replaces core/src/circuits.rs:9 and :31. */
+int zkb_verify_batch(zkb_engine *e, const zkb_email_view *emails, size_t n,
+                     const zkb_regex_set *regex, const zkb_email_captures *captures,
+                     zkb_result *out);
+/* Thin wrapper: batch of one (the reference's call shape). */
+int zkb_verify_one(zkb_engine *e, const zkb_email_view *email, const zkb_regex_set *regex,
+                   const zkb_email_captures *captures, zkb_result *out);
+
+/* Split form used by bench.py to time the device-resident pass separately:
+ *   prepare = host parse/canonicalise/pack + H2D;  run = kernels only (inputs resident in HBM);
+ *   fetch = D2H + host post-processing into zkb_result records. */
+int zkb_batch_prepare(zkb_engine *e, const zkb_email_view *emails, size_t n,
+                      const zkb_regex_set *regex, const zkb_email_captures *captures,
+                      zkb_batch **out);
+int zkb_batch_run(zkb_batch *b);                 /* enqueue + synchronise */
+int zkb_batch_run_async(zkb_batch *b);           /* enqueue only on the engine stream */
+int zkb_batch_fetch(zkb_batch *b, zkb_result *out);
+void zkb_batch_destroy(zkb_batch *b);
+/* Work actually resident for this batch (for the roofline arithmetic in bench.py). */
+typedef struct {
+  uint64_t n_emails, n_candidates, n_sha_messages, sha_blocks, sha_bytes;
+  uint64_t rsa_items_1024, rsa_items_2048, rsa_items_other, rsa_macs;
+  uint64_t dfa_items, dfa_bytes, arena_bytes, h2d_bytes, d2h_bytes;
+  uint64_t kernel_launches;          /* kernels one zkb_batch_run launches */
+} zkb_batch_stats;
+int zkb_batch_get_stats(const zkb_batch *b, zkb_batch_stats *out);
+/* CUDA-event time (ms) of the kernels of the last zkb_batch_run, per kernel family, measured on
+ * the engine stream: [0]=sha256 [1]=rsa [2]=dfa [3]=bh/finalize [4]=whole run */
+int zkb_batch_last_timing(const zkb_batch *b, float ms[5]);
+void *zkb_engine_stream(zkb_engine *e);          /* cudaStream_t of the engine */
+
+/* ---- regex compiler (stands in for helpers/src/regex.rs:7-51, which needs regex-automata) ----
+ * Compiles `pattern` (Rust-regex syntax subset, Unicode/UTF-8 mode as DFARegex::new) to forward
+ * and reverse ZDF1 tables.  On success *fwd/*bwd are malloc'ed; free with zkb_free. */
+int zkb_regex_compile(const char *pattern, size_t pattern_len, uint8_t **fwd, size_t *fwd_len,
+                      uint8_t **bwd, size_t *bwd_len, char *err, size_t err_cap);
+void zkb_free(void *p);
+
+/* ---- kernel-level entry points (host buffers in, host buffers out) for parity tests ---- */
+/* SHA-256 of n messages data[off[i] .. off[i]+len[i]) ; out = n x 32 bytes. */
+int zkb_sha256_batch(zkb_engine *e, const uint8_t *data, size_t data_len, const uint64_t *off,
+                     const uint32_t *len, size_t n, uint8_t *out);
+/* RSA PKCS#1 v1.5 SHA-256 verify of n items: key DER, 32-byte digest, signature bytes.
+ * ok[i] = 1 pass, 0 fail, 2 key rejected.  All keys may be distinct. */
+int zkb_rsa_verify_batch(zkb_engine *e, const uint8_t *const *key_der, const size_t *key_len,
+                         const uint8_t *digests, const uint8_t *const *sig, const size_t *sig_len,
+                         size_t n, uint8_t *ok);
+/* find_iter of one regex part over n haystacks; qp!=0 applies the soft-break cleaner on the fly.
+ * out = n x (count, start, end, flags). */
+int zkb_dfa_scan_batch(zkb_engine *e, const zkb_dfa_view *part, const uint8_t *data,
+                       size_t data_len, const uint64_t *off, const uint32_t *len, size_t n, int qp,
+                       uint32_t *out);
+/* Integer-pipe peak microbenchmarks (register-only): giga thread-instructions per second for
+ * [0]=IMAD.WIDE.U32 (dependent chains, 32x32+64) [1]=IADD3 [2]=LOP3 [3]=SHF  plus [4]=SM clock MHz
+ * observed by the kernel (clock64 vs events). Used as roofline denominators. */
+int zkb_int_pipe_peaks(zkb_engine *e, double out[8]);
+
+/*
+ * ZDF1 dense-DFA table layout (little-endian), the on-the-wire form of `DFA.fwd` / `DFA.bwd`:
+ *   0   u32 magic 0x3146445A ("ZDF1")
+ *   4   u32 flags: bit0 reverse, bit1 utf8 mode, bit2 pattern can match the empty string
+ *   8   u32 n_states           (state 0 is the dead state)
+ *   12  u32 n_classes          (byte classes + 1; the last class is end-of-input)
+ *   16  u32 min_match, 20 u32 max_match   (match states form the id range [min,max]; they are
+ *                                          entered one byte late, as in regex-automata)
+ *   24  u32 start[12]          (unanchored then anchored; kinds NonWordByte, WordByte, Text,
+ *                               LineLF, LineCR, CustomLineTerminator)
+ *   72  u8  class_map[256]
+ *   328 u8  start_map[256]     (look-behind byte -> start kind)
+ *   584 u32 trans[n_states * n_classes]
+ */
+#define ZKB_ZDF_MAGIC 0x3146445Au
+#define ZKB_ZDF_HEADER 584
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,46 @@
+// common.cuh — shared device/host definitions for the zkemail_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define ZKB_CUDA_OK(expr)                                                                    \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      fprintf(stderr, "[zkemail_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e),   \
+              __FILE__, __LINE__, cudaGetErrorString(_e));                                   \
+      return ZKB_E_CUDA;                                                                     \
+    }                                                                                        \
+  } while (0)
+
+// Key table entry layout (u32 words, little-endian limbs), one per unique public key.
+//   [0..127]   n      (zero padded to 128 limbs)
+//   [128..255] R^2 mod n, R = 2^(32*limbs)
+//   [256] n0inv = -n^-1 mod 2^32   [257] e low 32   [258] e high   [259] k = byte length of n
+//   [260] limbs class (32/64/96/128)   [261..263] reserved
+#define ZKB_KEY_STRIDE 264
+#define ZKB_KEY_RR 128
+#define ZKB_KEY_N0INV 256
+#define ZKB_KEY_ELO 257
+#define ZKB_KEY_EHI 258
+#define ZKB_KEY_K 259
+#define ZKB_KEY_LIMBS 260
+
+// One RSA work item (16 B, loaded as uint4 by every lane of the cooperating group).
+//   x: word offset of the signature (LE limbs, zero padded to the key's limb class) in sig arena
+//   y: key id   z: digest slot of the header hash   w: candidate slot (output)
+struct __align__(16) RsaItem {
+  uint32_t sig_off, key_id, digest_slot, cand;
+};
+
+// One DFA scan item. hay_off in bytes into the arena.
+struct __align__(16) DfaItem {
+  uint64_t hay_off;
+  uint32_t hay_len;
+  uint32_t out_slot;
+};
+
+// Per-candidate flags written by the device
+#define ZKB_F_RSA_OK 1u
+#define ZKB_F_BH_OK 2u

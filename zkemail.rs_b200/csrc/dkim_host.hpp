@@ -1,0 +1,447 @@
+// dkim_host.hpp — host front end of the engine: RFC 5322 header split (mailparse 0.15 rules),
+// DKIM-Signature tag-list parsing + validation, signed-header selection, simple/relaxed header and
+// body canonicalisation, base64.  This is the part of cfdkim::verify_email_with_key /
+// canonicalize_signed_email (core/src/email.rs:31-33, core/src/circuits.rs:34-35) that is byte
+// shuffling rather than arithmetic; everything it emits goes to the device kernels.
+// Semantics: SURVEY.md Appendix A.2.  Independent single-pass implementation (the oracle in
+// oracle/zk_oracle.c follows the reference's multi-pass operation order instead).
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <time.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/zkemail_b200.h"
+
+namespace zkb {
+
+struct HeaderField {
+  uint32_t key_off, key_len, val_off, val_len;
+};
+
+// mailparse::parse_headers.  false => parse_mail() would return Err (reference panics).
+inline bool parse_headers(const uint8_t* d, size_t n, std::vector<HeaderField>& out, size_t& body_off) {
+  out.clear();
+  size_t ix = 0;
+  while (ix < n) {
+    uint8_t c0 = d[ix];
+    if (c0 == '\n') { ix++; break; }
+    if (c0 == '\r') {
+      if (ix + 1 < n && d[ix + 1] == '\n') { ix += 2; break; }
+      return false;  // lone CR after the headers
+    }
+    if (c0 == ' ') return false;  // overhanging continuation line
+    // key: up to ':' ; a '\n' before any ':' makes a value-less header ending at that line
+    size_t p = ix;
+    while (p < n && d[p] != ':' && d[p] != '\n') p++;
+    HeaderField h;
+    h.key_off = (uint32_t)ix;
+    if (p >= n) {  // ran out of input inside the key: empty key, empty value
+      h.key_len = 0; h.val_off = (uint32_t)ix; h.val_len = 0;
+      out.push_back(h);
+      ix = n;
+      break;
+    }
+    if (d[p] == '\n') {
+      h.key_len = (uint32_t)(p - ix); h.val_off = (uint32_t)p; h.val_len = 0;
+      out.push_back(h);
+      ix = p + 1;
+      continue;
+    }
+    h.key_len = (uint32_t)(p - ix);
+    p++;  // past ':'
+    while (p < n && d[p] == ' ') p++;
+    size_t vs = p, ve = p;
+    // value: until a '\n' not followed by SP/TAB; end = one past the last byte that is not CR/LF
+    for (;;) {
+      const uint8_t* nl = (const uint8_t*)memchr(d + p, '\n', n - p);
+      size_t q = nl ? (size_t)(nl - d) : n;
+      // last non-CR byte in [p,q)
+      size_t e = q;
+      while (e > p && d[e - 1] == '\r') e--;
+      if (e > p) ve = e;
+      if (!nl) { p = n; break; }
+      p = q + 1;
+      if (p < n && (d[p] == ' ' || d[p] == '\t')) continue;
+      break;
+    }
+    if (ve < vs) ve = vs;
+    h.val_off = (uint32_t)vs; h.val_len = (uint32_t)(ve - vs);
+    out.push_back(h);
+    ix = p;
+  }
+  body_off = ix;
+  return true;
+}
+
+inline bool ieq_ascii(const uint8_t* a, size_t al, const char* b, size_t bl) {
+  if (al != bl) return false;
+  for (size_t i = 0; i < al; i++) {
+    uint8_t x = a[i], y = (uint8_t)b[i];
+    if (x - 'A' < 26u) x += 32;
+    if (y - 'A' < 26u) y += 32;
+    if (x != y) return false;
+  }
+  return true;
+}
+
+// String::from_utf8_lossy (only called when a byte >= 0x80 is present)
+inline void utf8_lossy(const uint8_t* in, size_t n, std::string& out) {
+  out.clear();
+  size_t i = 0;
+  auto at = [&](size_t k) -> uint8_t { return k < n ? in[k] : 0; };
+  while (i < n) {
+    uint8_t b = in[i];
+    size_t w = 0, bad = 1;
+    if (b < 0x80) w = 1;
+    else if (b >= 0xC2 && b <= 0xDF) { if ((at(i + 1) & 0xC0) == 0x80) w = 2; }
+    else if (b >= 0xE0 && b <= 0xEF) {
+      uint8_t c = at(i + 1);
+      bool ok2 = b == 0xE0 ? (c >= 0xA0 && c <= 0xBF) : b == 0xED ? (c >= 0x80 && c <= 0x9F) : (c >= 0x80 && c <= 0xBF);
+      if (ok2) { if ((at(i + 2) & 0xC0) == 0x80) w = 3; else bad = 2; }
+    } else if (b >= 0xF0 && b <= 0xF4) {
+      uint8_t c = at(i + 1);
+      bool ok2 = b == 0xF0 ? (c >= 0x90 && c <= 0xBF) : b == 0xF4 ? (c >= 0x80 && c <= 0x8F) : (c >= 0x80 && c <= 0xBF);
+      if (ok2) {
+        if ((at(i + 2) & 0xC0) != 0x80) bad = 2;
+        else if ((at(i + 3) & 0xC0) != 0x80) bad = 3;
+        else w = 4;
+      }
+    }
+    if (w) { out.append((const char*)in + i, w); i += w; }
+    else { out.append("\xEF\xBF\xBD", 3); i += bad; }
+  }
+}
+
+// ------------------------------------------------------------------ tag list
+struct Tag {
+  uint32_t name_off, name_len;
+  uint32_t raw_off, raw_len;   // value text with inner FWS kept (slice of the header value)
+  uint32_t val_off, val_len;   // value with FWS removed (slice of DkimSig::vals)
+};
+struct DkimSig {
+  const uint8_t* s = nullptr;  // header value (lossy utf-8 if it had non-ASCII bytes)
+  size_t n = 0;
+  std::string lossy, vals;
+  std::vector<Tag> tags;
+  const Tag* get(const char* name) const {
+    size_t l = strlen(name);
+    for (const Tag& t : tags)
+      if (t.name_len == l && memcmp(s + t.name_off, name, l) == 0) return &t;
+    return nullptr;
+  }
+  const uint8_t* val(const Tag* t) const { return (const uint8_t*)vals.data() + t->val_off; }
+  bool val_is(const Tag* t, const char* lit) const {
+    size_t l = strlen(lit);
+    return t->val_len == l && memcmp(val(t), lit, l) == 0;
+  }
+};
+
+namespace detail {
+inline bool fws(uint8_t c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n'; }
+inline bool valchar(uint8_t c) { return (c >= 0x21 && c <= 0x3A) || (c >= 0x3C && c <= 0x7E); }
+inline bool alpha(uint8_t c) { return (uint8_t)((c | 32) - 'a') < 26; }
+inline bool alnum_(uint8_t c) { return alpha(c) || (uint8_t)(c - '0') < 10 || c == '_'; }
+}  // namespace detail
+
+// cfdkim parser::tag_list + lib.rs::validate_header.  Returns ZKB_DKIM_PASS or the error kind.
+inline int validate_dkim_header(const uint8_t* raw_val, size_t raw_len, int64_t now_unix, DkimSig& sig) {
+  using namespace detail;
+  sig.tags.clear();
+  sig.vals.clear();
+  bool ascii = true;
+  for (size_t i = 0; i < raw_len; i++) if (raw_val[i] & 0x80) { ascii = false; break; }
+  if (ascii) { sig.s = raw_val; sig.n = raw_len; }
+  else { utf8_lossy(raw_val, raw_len, sig.lossy); sig.s = (const uint8_t*)sig.lossy.data(); sig.n = sig.lossy.size(); }
+  const uint8_t* s = sig.s;
+  const size_t n = sig.n;
+  size_t pos = 0;
+  bool first = true;
+  for (;;) {
+    size_t save_vals = sig.vals.size();
+    size_t p = pos;
+    if (!first) {
+      if (p >= n || s[p] != ';') break;
+      p++;
+    }
+    while (p < n && fws(s[p])) p++;
+    if (p >= n || !alpha(s[p])) { if (first) return ZKB_DKIM_SYNTAX; break; }
+    Tag t;
+    t.name_off = (uint32_t)p;
+    while (p < n && alnum_(s[p])) p++;
+    t.name_len = (uint32_t)(p - t.name_off);
+    while (p < n && fws(s[p])) p++;
+    if (p >= n || s[p] != '=') { if (first) return ZKB_DKIM_SYNTAX; break; }
+    p++;
+    while (p < n && fws(s[p])) p++;
+    t.raw_off = (uint32_t)p; t.raw_len = 0;
+    t.val_off = (uint32_t)sig.vals.size();
+    if (p < n && valchar(s[p])) {
+      for (;;) {
+        size_t a = p;
+        while (p < n && valchar(s[p])) p++;
+        sig.vals.append((const char*)s + a, p - a);
+        t.raw_len = (uint32_t)(p - t.raw_off);
+        size_t q = p;
+        while (q < n && fws(s[q])) q++;
+        if (q == p || q >= n || !valchar(s[q])) break;
+        p = q;
+      }
+    }
+    t.val_len = (uint32_t)(sig.vals.size() - t.val_off);
+    while (p < n && fws(s[p])) p++;
+    (void)save_vals;
+    // IndexMap insert: a later duplicate replaces the value in the first one's position
+    bool dup = false;
+    for (Tag& o : sig.tags)
+      if (o.name_len == t.name_len && memcmp(s + o.name_off, s + t.name_off, t.name_len) == 0) { o = t; dup = true; break; }
+    if (!dup) sig.tags.push_back(t);
+    pos = p;
+    first = false;
+  }
+  static const char* REQ[] = {"v", "a", "b", "bh", "d", "h", "s"};
+  for (const char* r : REQ) if (!sig.get(r)) return ZKB_DKIM_MISSING_TAG;
+  if (!sig.val_is(sig.get("v"), "1")) return ZKB_DKIM_VERSION;
+  const Tag* td = sig.get("d");
+  if (const Tag* ti = sig.get("i")) {
+    if (ti->val_len < td->val_len || memcmp(sig.val(ti) + ti->val_len - td->val_len, sig.val(td), td->val_len) != 0)
+      return ZKB_DKIM_DOMAIN_MISMATCH;
+  }
+  {
+    const Tag* th = sig.get("h");
+    const uint8_t* v = sig.val(th);
+    bool found = false;
+    size_t a = 0;
+    for (size_t i = 0; i <= th->val_len; i++)
+      if (i == th->val_len || v[i] == ':') { if (ieq_ascii(v + a, i - a, "from", 4)) found = true; a = i + 1; }
+    if (!found) return ZKB_DKIM_FROM_NOT_SIGNED;
+  }
+  if (const Tag* tq = sig.get("q")) if (!sig.val_is(tq, "dns/txt")) return ZKB_DKIM_QUERY_METHOD;
+  if (const Tag* tx = sig.get("x")) {
+    const uint8_t* v = sig.val(tx);
+    size_t l = tx->val_len, i = 0;
+    bool ok = l > 0, neg = false;
+    int64_t x = 0;
+    if (ok && (v[0] == '+' || v[0] == '-')) { neg = v[0] == '-'; i = 1; ok = l > 1; }
+    for (; ok && i < l; i++) {
+      if (v[i] < '0' || v[i] > '9') { ok = false; break; }
+      int dgt = v[i] - '0';
+      if (!neg) { if (x > (INT64_MAX - dgt) / 10) { ok = false; break; } x = x * 10 + dgt; }
+      else { if (x < (INT64_MIN + dgt) / 10) { ok = false; break; } x = x * 10 - dgt; }
+    }
+    if (!ok) x = 0;
+    int64_t now = now_unix ? now_unix : (int64_t)time(nullptr);
+    if (now > x + 15 * 60) return ZKB_DKIM_EXPIRED;
+  }
+  return ZKB_DKIM_PASS;
+}
+
+// c= tag.  false => UnsupportedCanonicalizationType
+inline bool parse_canon_tag(const DkimSig& sig, bool& hdr_relaxed, bool& body_relaxed) {
+  const Tag* tc = sig.get("c");
+  if (!tc) { hdr_relaxed = false; body_relaxed = false; return true; }
+  if (sig.val_is(tc, "relaxed/relaxed")) { hdr_relaxed = true; body_relaxed = true; }
+  else if (sig.val_is(tc, "simple/simple") || sig.val_is(tc, "simple")) { hdr_relaxed = false; body_relaxed = false; }
+  else if (sig.val_is(tc, "relaxed/simple") || sig.val_is(tc, "relaxed")) { hdr_relaxed = true; body_relaxed = false; }
+  else if (sig.val_is(tc, "simple/relaxed")) { hdr_relaxed = false; body_relaxed = true; }
+  else return false;
+  return true;
+}
+
+// usize::from_str for the l= tag
+inline bool parse_usize_tag(const DkimSig& sig, const Tag* t, uint64_t& out) {
+  const uint8_t* v = sig.val(t);
+  size_t i = 0;
+  if (t->val_len && v[0] == '+') i = 1;
+  if (i >= t->val_len) return false;
+  uint64_t x = 0;
+  for (; i < t->val_len; i++) {
+    if (v[i] < '0' || v[i] > '9') return false;
+    if (x > (UINT64_MAX - (v[i] - '0')) / 10) return false;
+    x = x * 10 + (v[i] - '0');
+  }
+  out = x;
+  return true;
+}
+
+// ------------------------------------------------------------------ canonicalisation (single pass)
+// Relaxed body; out must hold n + 2 bytes.
+inline size_t canon_body_relaxed(const uint8_t* in, size_t n, uint8_t* out) {
+  size_t o = 0;
+  bool prev_sp = false;
+  for (size_t i = 0; i < n; i++) {
+    uint8_t c = in[i];
+    if (c == ' ' || c == '\t') {
+      if (!prev_sp) { out[o++] = ' '; prev_sp = true; }
+      continue;
+    }
+    prev_sp = false;
+    if (c == '\n' && o >= 2 && out[o - 1] == '\r' && out[o - 2] == ' ') {
+      out[o - 2] = '\r'; out[o - 1] = '\n';  // drop the single SP before CRLF
+      continue;
+    }
+    out[o++] = c;
+  }
+  while (o >= 4 && out[o - 1] == '\n' && out[o - 2] == '\r' && out[o - 3] == '\n' && out[o - 4] == '\r') o -= 2;
+  if (o > 0 && !(o >= 2 && out[o - 2] == '\r' && out[o - 1] == '\n')) { out[o++] = '\r'; out[o++] = '\n'; }
+  return o;
+}
+inline size_t canon_body_simple(const uint8_t* in, size_t n, uint8_t* out) {
+  if (n == 0) { out[0] = '\r'; out[1] = '\n'; return 2; }
+  while (n >= 4 && in[n - 1] == '\n' && in[n - 2] == '\r' && in[n - 3] == '\n' && in[n - 4] == '\r') n -= 2;
+  memcpy(out, in, n);
+  return n;
+}
+inline bool latin1_ws(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13) || c == 0x85 || c == 0xA0; }
+inline size_t put_key(const uint8_t* key, size_t klen, uint8_t* out, bool lower) {
+  size_t o = 0;
+  for (size_t i = 0; i < klen; i++) {
+    uint32_t c = key[i];
+    if (lower) {
+      if (c - 'A' < 26u) c += 32;
+      else if (c >= 0xC0 && c <= 0xDE && c != 0xD7) c += 32;
+    }
+    if (c < 0x80) out[o++] = (uint8_t)c;
+    else { out[o++] = (uint8_t)(0xC0 | (c >> 6)); out[o++] = (uint8_t)(0x80 | (c & 0x3F)); }
+  }
+  return o;
+}
+// out must hold 2*klen + vlen + 3
+inline size_t canon_header_relaxed(const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen, uint8_t* out) {
+  while (klen > 0 && latin1_ws(key[klen - 1])) klen--;
+  size_t o = put_key(key, klen, out, true);
+  out[o++] = ':';
+  size_t start = o;
+  bool prev_sp = true;  // swallows leading SP
+  for (size_t i = 0; i < vlen; i++) {
+    uint8_t c = val[i];
+    if (c == '\r' && i + 1 < vlen && val[i + 1] == '\n') { i++; continue; }
+    if (c == ' ' || c == '\t') {
+      if (!prev_sp) { out[o++] = ' '; prev_sp = true; }
+      continue;
+    }
+    prev_sp = false;
+    out[o++] = c;
+  }
+  if (o > start && out[o - 1] == ' ') o--;
+  out[o++] = '\r'; out[o++] = '\n';
+  return o;
+}
+inline size_t canon_header_simple(const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen, uint8_t* out) {
+  size_t o = put_key(key, klen, out, false);
+  out[o++] = ':'; out[o++] = ' ';
+  memcpy(out + o, val, vlen); o += vlen;
+  out[o++] = '\r'; out[o++] = '\n';
+  return o;
+}
+
+// Upper bound of the header-hash preimage for a message whose header block is `hdr_bytes` long.
+inline size_t preimage_bound(size_t hdr_bytes, size_t sig_val_len) { return 2 * hdr_bytes + 3 * sig_val_len + 64; }
+
+// select_headers + canonicalise + the b-less DKIM-Signature (no trailing CRLF). Returns length.
+inline size_t build_header_preimage(const uint8_t* raw, const std::vector<HeaderField>& hs, const DkimSig& sig,
+                                    bool relaxed, uint8_t* out, std::string& scratch) {
+  const Tag* th = sig.get("h");
+  const uint8_t* hv = sig.val(th);
+  size_t o = 0;
+  struct Cur { uint32_t off, len; long idx; };
+  Cur last[64];
+  int n_last = 0;
+  std::vector<Cur> more;  // beyond 64 distinct names (pathological)
+  size_t a = 0;
+  for (size_t i = 0; i <= th->val_len; i++) {
+    if (i != th->val_len && hv[i] != ':') continue;
+    size_t s = a, e = i;
+    a = i + 1;
+    while (s < e && (hv[s] == ' ' || (hv[s] >= 9 && hv[s] <= 13))) s++;  // cannot occur (FWS stripped)
+    while (e > s && (hv[e - 1] == ' ' || (hv[e - 1] >= 9 && hv[e - 1] <= 13))) e--;
+    if (s == e) continue;
+    long start = (long)hs.size();
+    Cur* cur = nullptr;
+    for (int k = 0; k < n_last; k++)
+      if (ieq_ascii(hv + last[k].off, last[k].len, (const char*)hv + s, e - s)) { cur = &last[k]; break; }
+    if (!cur) for (Cur& c : more) if (ieq_ascii(hv + c.off, c.len, (const char*)hv + s, e - s)) { cur = &c; break; }
+    if (cur) start = cur->idx;
+    long hit = -1;
+    for (long j = start - 1; j >= 0; j--)
+      if (ieq_ascii(raw + hs[j].key_off, hs[j].key_len, (const char*)hv + s, e - s)) { hit = j; break; }
+    if (!cur) {
+      if (n_last < 64) cur = &last[n_last++];
+      else { more.push_back(Cur{}); cur = &more.back(); }
+      cur->off = (uint32_t)s; cur->len = (uint32_t)(e - s);
+    }
+    cur->idx = hit >= 0 ? hit : 0;
+    if (hit >= 0) {
+      const HeaderField& h = hs[hit];
+      o += relaxed ? canon_header_relaxed(raw + h.key_off, h.key_len, raw + h.val_off, h.val_len, out + o)
+                   : canon_header_simple(raw + h.key_off, h.key_len, raw + h.val_off, h.val_len, out + o);
+    }
+  }
+  // the signature header with every occurrence of the raw b= text removed
+  const Tag* tb = sig.get("b");
+  const uint8_t* v = sig.s;
+  size_t vl = sig.n;
+  if (tb->raw_len != 0) {
+    scratch.clear();
+    const uint8_t* pat = sig.s + tb->raw_off;
+    size_t pl = tb->raw_len, i = 0;
+    while (i < vl) {
+      const uint8_t* f = (i + pl <= vl) ? (const uint8_t*)memmem(sig.s + i, vl - i, pat, pl) : nullptr;
+      if (!f) { scratch.append((const char*)sig.s + i, vl - i); break; }
+      scratch.append((const char*)sig.s + i, (size_t)(f - (sig.s + i)));
+      i = (size_t)(f - sig.s) + pl;
+    }
+    v = (const uint8_t*)scratch.data(); vl = scratch.size();
+  }
+  size_t w = relaxed ? canon_header_relaxed((const uint8_t*)"DKIM-Signature", 14, v, vl, out + o)
+                     : canon_header_simple((const uint8_t*)"DKIM-Signature", 14, v, vl, out + o);
+  return o + w - 2;
+}
+
+// bytes::get_all_after(raw, "\r\n\r\n")
+inline const uint8_t* find_body(const uint8_t* raw, size_t n, size_t& blen) {
+  const uint8_t* f = n >= 4 ? (const uint8_t*)memmem(raw, n, "\r\n\r\n", 4) : nullptr;
+  if (!f) { blen = 0; return raw + n; }
+  blen = n - (size_t)(f - raw) - 4;
+  return f + 4;
+}
+
+// ------------------------------------------------------------------ base64 (STANDARD, strict)
+struct B64 {
+  int8_t t[256];
+  B64() {
+    memset(t, -1, sizeof t);
+    const char* a = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+    for (int i = 0; i < 64; i++) t[(uint8_t)a[i]] = (int8_t)i;
+  }
+};
+inline const B64& b64tab() { static const B64 t; return t; }
+// returns decoded length or -1.  out needs 3*n/4 bytes.
+inline long base64_decode(const uint8_t* in, size_t n, uint8_t* out) {
+  if (n % 4) return -1;
+  const int8_t* T = b64tab().t;
+  size_t o = 0;
+  for (size_t i = 0; i < n; i += 4) {
+    int a = T[in[i]], b = T[in[i + 1]], c = T[in[i + 2]], d = T[in[i + 3]];
+    if ((a | b | c | d) >= 0) {
+      out[o++] = (uint8_t)((a << 2) | (b >> 4));
+      out[o++] = (uint8_t)((b << 4) | (c >> 2));
+      out[o++] = (uint8_t)((c << 6) | d);
+      continue;
+    }
+    if (i + 4 != n || a < 0 || b < 0) return -1;
+    if (in[i + 2] == '=' && in[i + 3] == '=') {
+      if (b & 15) return -1;
+      out[o++] = (uint8_t)((a << 2) | (b >> 4));
+    } else if (in[i + 3] == '=' && c >= 0) {
+      if (c & 3) return -1;
+      out[o++] = (uint8_t)((a << 2) | (b >> 4));
+      out[o++] = (uint8_t)((b << 4) | (c >> 2));
+    } else return -1;
+  }
+  return (long)o;
+}
+
+}  // namespace zkb
