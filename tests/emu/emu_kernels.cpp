@@ -1,0 +1,114 @@
+// emu_kernels.cpp — TEST INFRASTRUCTURE: builds the product's kernel sources for the CPU through
+// tests/emu/emu_cuda.h and exposes them with a C ABI so the `not gpu` tests can check the very
+// source the GPU runs (SHA-256 lanes, cooperative Montgomery groups, DFA scans) against the
+// oracle, hashlib and Python big ints.
+#include "emu_cuda.h"
+
+#include "../../include/zkemail_b200.h"
+#include "../../zkemail.rs_b200/csrc/common.cuh"
+#include "../../zkemail.rs_b200/csrc/keytab.hpp"
+#include "../../zkemail.rs_b200/csrc/sha256.cuh"
+#include "../../zkemail.rs_b200/csrc/rsa.cuh"
+// dfa.cuh added below once rewritten
+
+using namespace zkb;
+
+template <int LIMBS, int T, bool G>
+static void run_rsa(const uint32_t* sig_arena, const RsaItem* items, uint32_t n_items,
+                    const uint32_t* keytab, const uint32_t* digests, uint32_t* flags) {
+  const unsigned block = 128;
+  unsigned threads = n_items * T;
+  emu::launch((threads + block - 1) / block, block, [&]() {
+    rsa_verify_kernel<LIMBS, T, G>(sig_arena, items, n_items, keytab, digests, flags);
+  });
+}
+
+extern "C" {
+
+void emu_sha256_batch(const uint8_t* arena, const uint64_t* off, const uint32_t* len,
+                      const uint32_t* order, uint32_t n, uint32_t* digests) {
+  const unsigned block = 128;
+  emu::launch((n + block - 1) / block, block,
+              [&]() { sha256_batch_kernel(arena, off, len, order, n, digests); });
+}
+
+// key DER -> key-table entry (ZKB_KEY_STRIDE words). returns 0 ok, 1 rejected
+int emu_build_key_entry(const uint8_t* der, size_t len, uint32_t* ent) {
+  RsaKeyInfo k;
+  if (!parse_rsa_public_key(der, len, k)) return 1;
+  build_key_entry(k, ent);
+  return 0;
+}
+
+int emu_rsa_verify(int limbs, int T, int generic, const uint32_t* sig_arena, const void* items,
+                   uint32_t n_items, const uint32_t* keytab, const uint32_t* digests,
+                   uint32_t* flags) {
+  const RsaItem* it = (const RsaItem*)items;
+#define CASE(LB, TT)                                                                        \
+  if (limbs == LB && T == TT) {                                                             \
+    if (generic) run_rsa<LB, TT, true>(sig_arena, it, n_items, keytab, digests, flags);     \
+    else run_rsa<LB, TT, false>(sig_arena, it, n_items, keytab, digests, flags);            \
+    return 0;                                                                               \
+  }
+  CASE(32, 2) CASE(32, 4) CASE(32, 8) CASE(32, 16)
+  CASE(64, 2) CASE(64, 4) CASE(64, 8) CASE(64, 16) CASE(64, 32)
+  CASE(128, 8) CASE(128, 16) CASE(128, 32)
+#undef CASE
+  return 1;
+}
+
+}  // extern "C"
+
+// ---- regex compiler + DFA kernel ----
+#include "../../zkemail.rs_b200/csrc/regexc.hpp"
+#include "../../zkemail.rs_b200/csrc/dfa_host.hpp"
+
+extern "C" {
+
+// returns 0 ok; *fwd/*bwd malloc'ed (free with emu_free)
+int emu_regex_compile(const char* pat, size_t len, uint8_t** fwd, size_t* fl, uint8_t** bwd, size_t* bl,
+                      char* err, size_t err_cap) {
+  std::vector<uint8_t> f, b;
+  std::string e;
+  if (!rx::compile(pat, len, f, b, e)) {
+    if (err && err_cap) { strncpy(err, e.c_str(), err_cap - 1); err[err_cap - 1] = 0; }
+    return 1;
+  }
+  *fwd = (uint8_t*)malloc(f.size()); memcpy(*fwd, f.data(), f.size()); *fl = f.size();
+  *bwd = (uint8_t*)malloc(b.size()); memcpy(*bwd, b.data(), b.size()); *bl = b.size();
+  return 0;
+}
+void emu_free(void* p) { free(p); }
+
+// out = n x uint4 (count, start, end, panic)
+int emu_dfa_scan(const uint8_t* fwd, size_t fl, const uint8_t* bwd, size_t bl, const uint8_t* arena,
+                 const uint64_t* off, const uint32_t* len, uint32_t n, int qp, int use_smem, uint32_t* out) {
+  std::vector<uint8_t> fb, rb;
+  uint32_t fe, re;
+  if (!build_dfa_blob(fwd, fl, false, fb, fe) || !build_dfa_blob(bwd, bl, true, rb, re)) return 1;
+  std::vector<DfaItem> items(n);
+  for (uint32_t i = 0; i < n; i++) { items[i].hay_off = off[i]; items[i].hay_len = len[i]; items[i].out_slot = i; }
+  const unsigned block = 128;
+  bool wide = fe == 4 || re == 4;
+  if (wide) {  // the kernel uses one element width for both tables
+    std::vector<uint8_t> t;
+    // re-encode a 16-bit table as 32-bit
+    auto widen = [&](std::vector<uint8_t>& b, uint32_t e) {
+      if (e == 4) return;
+      size_t cells = (size_t)((uint32_t*)b.data())[0] * ((uint32_t*)b.data())[1];
+      t.assign((ZKB_DFA_HDR + cells * 4 + 15) & ~(size_t)15, 0);
+      memcpy(t.data(), b.data(), ZKB_DFA_HDR);
+      ((uint32_t*)t.data())[5] = 4;
+      for (size_t i = 0; i < cells; i++) ((uint32_t*)(t.data() + ZKB_DFA_HDR))[i] = ((uint16_t*)(b.data() + ZKB_DFA_HDR))[i];
+      b.swap(t);
+    };
+    widen(fb, fe); widen(rb, re);
+  }
+  emu::launch((n + block - 1) / block, block, [&]() {
+    if (wide) dfa_scan_kernel<uint32_t>(arena, items.data(), n, fb.data(), (uint32_t)fb.size(), rb.data(), (uint32_t)rb.size(), use_smem, qp, (uint4*)out);
+    else dfa_scan_kernel<uint16_t>(arena, items.data(), n, fb.data(), (uint32_t)fb.size(), rb.data(), (uint32_t)rb.size(), use_smem, qp, (uint4*)out);
+  });
+  return 0;
+}
+
+}  // extern "C"

@@ -1,6 +1,8 @@
 // common.cuh — shared device/host definitions for the zkemail_b200 kernels (sm_100a only).
 #pragma once
+#ifndef ZKB_HOST_EMU
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 

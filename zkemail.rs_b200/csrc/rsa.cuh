@@ -27,6 +27,7 @@
 
 namespace zkb {
 
+#ifndef ZKB_HOST_EMU
 // (d0,d1) = a*b + (c0,c1)            ; sets CC.   d must not alias inputs (3-operand form)
 #define ZKB_MADW_FIRST(d0, d1, a, b, c0, c1)                                                 \
   asm volatile("mad.lo.cc.u32 %0, %2, %3, %4;\n\tmadc.hi.cc.u32 %1, %2, %3, %5;"             \
@@ -48,6 +49,18 @@ namespace zkb {
 #define ZKB_SUB_CC(d, a) asm volatile("sub.cc.u32 %0, %0, %1;" : "+r"(d) : "r"(a))
 #define ZKB_SUBC_CC(d, a) asm volatile("subc.cc.u32 %0, %0, %1;" : "+r"(d) : "r"(a))
 #define ZKB_SUBC(d, a) asm volatile("subc.u32 %0, %0, %1;" : "+r"(d) : "r"(a))
+#else  // host emulation of the same PTX semantics (tests/emu/emu_cuda.h)
+#define ZKB_MADW_FIRST(d0, d1, a, b, c0, c1) emu::madw(d0, d1, a, b, c0, c1, false)
+#define ZKB_MADW_CC(d0, d1, a, b, c0, c1) emu::madw(d0, d1, a, b, c0, c1, true)
+#define ZKB_MACW_FIRST(d0, d1, a, b) emu::madw(d0, d1, a, b, d0, d1, false)
+#define ZKB_MACW_CC(d0, d1, a, b) emu::madw(d0, d1, a, b, d0, d1, true)
+#define ZKB_ADD_CC(d, a) emu::addc(d, a, false, true)
+#define ZKB_ADDC_CC(d, a) emu::addc(d, a, true, true)
+#define ZKB_ADDC(d, a) emu::addc(d, a, true, false)
+#define ZKB_SUB_CC(d, a) emu::subc(d, a, false, true)
+#define ZKB_SUBC_CC(d, a) emu::subc(d, a, true, true)
+#define ZKB_SUBC(d, a) emu::subc(d, a, true, false)
+#endif
 
 template <int L, int T>
 struct Mont {
@@ -168,16 +181,16 @@ struct Mont {
     const unsigned gm = (T >= 32) ? 0xffffffffu : ((1u << T) - 1u);
     unsigned g = (G >> group_shift) & gm, p = (P >> group_shift) & gm;
     p &= ~g;
-    unsigned s = g + (g | p);
-    unsigned cins = s ^ (g ^ (g | p));  // bit q = carry into lane q, bit T = carry out of the group
-    uint32_t cin = (cins >> lane_in_group) & 1u;
+    unsigned long long s = (unsigned long long)g + (g | p);
+    unsigned long long cins = s ^ (g ^ (g | p));  // bit q = carry into lane q, bit T = carry out
+    uint32_t cin = (uint32_t)(cins >> lane_in_group) & 1u;
     if (T > 1) {
       ZKB_ADD_CC(r[0], cin);
 #pragma unroll
       for (int j = 1; j < L; j++) ZKB_ADDC_CC(r[j], 0u);
     }
     // overflow beyond R: hi of the top lane + carry out
-    uint32_t ov_top = hi0 + ((cins >> T) & 1u);  // hi1 is provably zero on the top lane
+    uint32_t ov_top = hi0 + ((uint32_t)(cins >> T) & 1u);  // hi1 is provably zero on the top lane
     uint32_t ov = __shfl_sync(FULL, ov_top, T - 1, T);
     cond_sub(r, n, ov != 0, lane_in_group, group_shift);
   }
