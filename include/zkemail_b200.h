@@ -170,6 +170,17 @@ int zkb_regex_compile(const char *pattern, size_t pattern_len, uint8_t **fwd, si
                       uint8_t **bwd, size_t *bwd_len, char *err, size_t err_cap);
 void zkb_free(void *p);
 
+/* ---- host-only utility: cfdkim::canonicalize_signed_email (core/src/circuits.rs:34-35,
+ * helpers/src/generator.rs:63) ----
+ * Returns the header-hash preimage and the canonical body of the first valid DKIM-Signature header
+ * (the regex haystacks before the quoted-printable clean-up).  Needs no device (pure byte work, the
+ * same code the batch path runs on its host threads).  *hdr / *body are malloc'ed; free with
+ * zkb_free.  Returns ZKB_OK, or ZKB_E_INVALID when the reference's unwrap() would panic
+ * (*detail = 1 parse error, 2 no valid signature, 3 bad c=, 4 bad l=, 5 bad b= base64). */
+int zkb_host_canonicalize(const uint8_t *raw_email, size_t raw_email_len, int64_t now_unix,
+                          uint8_t **hdr, size_t *hdr_len, uint8_t **body, size_t *body_len,
+                          int *detail);
+
 /* ---- kernel-level entry points (host buffers in, host buffers out) for parity tests ---- */
 /* SHA-256 of n messages data[off[i] .. off[i]+len[i]) ; out = n x 32 bytes. */
 int zkb_sha256_batch(zkb_engine *e, const uint8_t *data, size_t data_len, const uint64_t *off,

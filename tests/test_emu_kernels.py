@@ -1,0 +1,199 @@
+"""The kernel SOURCES (sha256.cuh, rsa.cuh, dfa.cuh) compiled for the host through tests/emu and
+checked against hashlib / the oracle / Python big ints.  This box has no GPU; the emulation runs
+the same source lines (warp shuffles, ballots, PTX carry chains emulated) so that arithmetic and
+control-flow bugs are caught before GPU time is spent.  The -m gpu tests remain the authority."""
+import hashlib
+import math
+import re
+
+import numpy as np
+import pytest
+from cryptography.hazmat.primitives import hashes
+from cryptography.hazmat.primitives.asymmetric import padding
+
+import oracle
+from tests import emu
+from tests.util import key_pool
+
+
+def test_sha256_kernel_source():
+    rng = np.random.default_rng(1)
+    lens = [0, 1, 3, 55, 56, 57, 63, 64, 65, 119, 120, 127, 128, 129, 4096, 4097, 520, 1000]
+    lens += [int(x) for x in rng.integers(0, 700, size=110)]
+    msgs = [rng.integers(0, 256, size=l, dtype=np.uint8).tobytes() for l in lens]
+    got = emu.sha256_batch(msgs)
+    for m, g in zip(msgs, got):
+        assert g == hashlib.sha256(m).digest(), len(m)
+
+
+def _rsa_cases(bits, n):
+    keys = key_pool()[bits]
+    ks, ds, ss, exp = [], [], [], []
+    for i in range(n):
+        k = keys[i % len(keys)]
+        m = b"msg%d" % i
+        sig = k.private.sign(m, padding.PKCS1v15(), hashes.SHA256())
+        d = hashlib.sha256(m).digest()
+        kind = i % 6
+        if kind == 1:
+            sig = bytes([sig[0] ^ 1]) + sig[1:]
+        elif kind == 2:
+            d = hashlib.sha256(m + b"x").digest()
+        elif kind == 3:
+            sig = b"\xff" * len(sig)   # s >= n
+        elif kind == 4:
+            sig = b"\x00" * len(sig)
+        ks.append(k.der); ds.append(d); ss.append(sig)
+        exp.append(1 if oracle.rsa_verify_sha256(k.der, d, sig) == 1 else 0)
+    return ks, ds, ss, exp
+
+
+@pytest.mark.parametrize("bits,limbs,lanes", [(2048, 64, 4), (2048, 64, 8), (2048, 64, 16), (1024, 32, 2),
+                                              (1024, 32, 4), (1024, 32, 8)])
+def test_rsa_kernel_source(bits, limbs, lanes):
+    ks, ds, ss, exp = _rsa_cases(bits, 12)
+    assert emu.rsa_verify(ks, ds, ss, limbs, lanes) == exp
+    assert sum(exp) >= 4
+
+
+def _prime(bits, rng):
+    def is_prime(n):
+        if n % 2 == 0:
+            return False
+        d, r = n - 1, 0
+        while d % 2 == 0:
+            d //= 2; r += 1
+        for a in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+            x = pow(a, d, n)
+            if x in (1, n - 1):
+                continue
+            for _ in range(r - 1):
+                x = x * x % n
+                if x == n - 1:
+                    break
+            else:
+                return False
+        return True
+    while True:
+        nb = (bits + 7) // 8
+        p = (int.from_bytes(rng.bytes(nb), "big") >> (8 * nb - bits)) | (1 << (bits - 1)) | 1
+        if all(p % q for q in (3, 5, 7, 11, 13, 17, 19, 23, 29, 31)) and is_prime(p):
+            return p
+
+
+def _der(n, e):
+    def ln(l):
+        return bytes([l]) if l < 128 else (b"\x81" + bytes([l]) if l < 256 else b"\x82" + l.to_bytes(2, "big"))
+    def integer(v):
+        b = v.to_bytes((v.bit_length() + 8) // 8, "big")
+        return b"\x02" + ln(len(b)) + b
+    body = integer(n) + integer(e)
+    return b"\x30" + ln(len(body)) + body
+
+
+@pytest.mark.parametrize("nbits,limbs,lanes,e", [(2047, 64, 8, 65537), (1536, 64, 4, 65537), (2048, 64, 8, 3),
+                                                 (1000, 32, 4, 17), (3072, 128, 16, 65537), (4096, 128, 8, 65537)])
+def test_rsa_kernel_source_odd_moduli_and_exponents(nbits, limbs, lanes, e):
+    """Moduli that do not fill their limb class, short moduli (k < 4*limbs) and e != 65537 (generic
+    ladder): hand-made keys, signatures forged with the private exponent."""
+    rng = np.random.default_rng(nbits + e)
+    while True:
+        p, q = _prime(nbits // 2, rng), _prime(nbits - nbits // 2, rng)
+        n = p * q
+        phi = (p - 1) * (q - 1)
+        if n.bit_length() == nbits and math.gcd(e, phi) == 1:
+            break
+    d = pow(e, -1, phi)
+    k = (nbits + 7) // 8
+    der = _der(n, e)
+    ks, ds, ss, exp = [], [], [], []
+    for i in range(6):
+        h = hashlib.sha256(b"m%d" % i).digest()
+        em = b"\x00\x01" + b"\xff" * (k - 54) + b"\x00" + bytes.fromhex("3031300d060960864801650304020105000420") + h
+        s = pow(int.from_bytes(em, "big"), d, n)
+        if i == 1:
+            s ^= 1 << 7
+        if i == 2:
+            h = hashlib.sha256(b"other").digest()
+        ks.append(der); ds.append(h); ss.append(s.to_bytes(k, "big"))
+        exp.append(1 if oracle.rsa_verify_sha256(der, h, ss[-1]) == 1 else 0)
+    assert exp == [1, 0, 0, 1, 1, 1]
+    assert emu.rsa_verify(ks, ds, ss, limbs, lanes, generic=(e != 65537)) == exp
+
+
+RUST_PY = [(rb"abc", None), (rb"a+", None), (rb"a*", None), (rb"[a-c]+d", None), (rb"(a|ab)(c|bcd)", None),
+           (rb"from:[^\r\n]*@example\.com", None), (rb"subject:[^\r\n]+", None), (rb"Transaction ID: [A-Z0-9]+", None),
+           (rb"(?i)hello", None), (rb"a{2,4}", None), (rb"a{2,4}?", None), (rb"a{3}", None), (rb"a{2,}b", None),
+           (rb"x*?y", None), (rb"^abc", None), (rb"abc$", None), (rb"(?m)^a+$", None), (rb"\d+\.\d+", None),
+           (rb"[^a]+", None), (rb".", None), (rb".*", None), (rb".+?b", None), (rb"(?s).+", None),
+           (rb"\w+@\w+\.com", None), (rb"(foo|foobar|fo)", None), (rb"(?:ab)*c", None),
+           (rb"[[:alpha:]]+", rb"[A-Za-z]+"), (rb"\x41+", None), (rb"a|b|", None), (rb"\Aab|cd\z", rb"\Aab|cd\Z"),
+           (rb"(?i)[k-s]+", None), (rb"a?b?c?", None), (rb"(a*)*b", None), (rb"(a|b)*?c", None), (rb"\s+", None),
+           (rb"to:[^\r\n]+\r\n", None), (rb"(?P<n>a)(?<m>b)", rb"(?P<n>a)(?P<m>b)"), (rb"[\]\[]+", None),
+           (rb"(?U)a+", rb"a+?"), (rb"a(?i)b|c", rb"a[bB]|[cC]")]
+
+
+def _py_spans(pat, hay):
+    out, last = [], None
+    for m in re.finditer(pat, hay):
+        s, e = m.span()
+        if s == e and last == e:   # Rust skips an empty match adjacent to the previous match
+            continue
+        out.append((s, e)); last = e
+    return out
+
+
+def _hays(seed):
+    rng = np.random.default_rng(seed)
+    alpha = b"abcdxy @.:\r\nAB019kK=\x00"
+    hays = [b"", b"a", b"abc", b"aaab", b"xabcabcx", b"from:bob <bob@example.com>\r\nsubject:hi there\r\nto:x\r\n",
+            b"Transaction ID: A1B2C3 ok", b"hello HELLO HeLLo", b"ab\nabc\naa\n", b"3.14 and 2.71", b"][]["]
+    for _ in range(70):
+        l = int(rng.integers(0, 40))
+        hays.append(bytes(alpha[i] for i in rng.integers(0, len(alpha), size=l)))
+    return hays
+
+
+@pytest.mark.parametrize("pat,pypat", RUST_PY)
+def test_regex_compiler_oracle_search_and_dfa_kernel_source(pat, pypat):
+    """pattern -> ZDF1 (regexc.hpp) -> spans: the oracle's find_iter and the DFA kernel source must
+    both equal Python `re` (leftmost-first, with Rust's empty-match iteration rule)."""
+    fwd, bwd = emu.regex_compile(pat)
+    hays = _hays(7)
+    exp = [_py_spans(pypat or pat, h) for h in hays]
+    for h, e in zip(hays, exp):
+        cnt, spans = oracle.dfa_find_iter(fwd, bwd, h, 64)
+        assert cnt == len(e) and spans == e[:64], (pat, h, e, spans)
+    got = emu.dfa_scan(fwd, bwd, hays, qp=False, use_smem=True)
+    for h, e, r in zip(hays, exp, got):
+        c, s, en, panic = (int(x) for x in r)
+        assert c == len(e) and not panic and (not e or (s, en) == e[0]), (pat, h, e, r)
+    # fused quoted-printable soft-break removal vs the oracle on the cleaned copy
+    hq = [h.replace(b"b", b"b=\r\n", 1) if i % 2 else h + b"=\r\n" for i, h in enumerate(hays)]
+    got = emu.dfa_scan(fwd, bwd, hq, qp=True, use_smem=False)
+    for h, r in zip(hq, got):
+        clean, _ = oracle.qp_clean(h)
+        cnt, spans = oracle.dfa_find_iter(fwd, bwd, clean, 4)
+        c, s, en, panic = (int(x) for x in r)
+        assert c == cnt and not panic and (not cnt or (s, en) == spans[0]), (pat, h, clean, spans, r)
+
+
+def test_regex_unicode_classes_utf8():
+    fwd, bwd = emu.regex_compile("é+|[α-ω]+|.".encode())
+    hay = "aéé βγ €\n".encode()
+    cnt, spans = oracle.dfa_find_iter(fwd, bwd, hay, 64)
+    exp = [m.span() for m in re.finditer("é+|[α-ω]+|.".encode().decode(), hay.decode())]
+    # convert character spans to byte spans
+    s = hay.decode()
+    b = lambda i: len(s[:i].encode())
+    assert spans == [(b(x), b(y)) for x, y in exp]
+    # negated class spans whole scalars, never a lone continuation byte
+    fwd, bwd = emu.regex_compile(rb"[^a]")
+    assert oracle.dfa_find_iter(fwd, bwd, "a€a".encode(), 8) == (1, [(1, 4)])
+    assert oracle.dfa_find_iter(fwd, bwd, b"a\xffa", 8) == (0, [])   # invalid UTF-8 never matches
+
+
+@pytest.mark.parametrize("bad", [rb"a(", rb"\bfoo", rb"[a", rb"*a", rb"\p{L}", rb"(?x)a", rb"a{5,2}", rb"(?-u:.)", rb"a)", rb"[z-a]", rb"\1"])
+def test_regex_compiler_rejects(bad):
+    with pytest.raises(ValueError):
+        emu.regex_compile(bad)

@@ -1,0 +1,156 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI of
+libzkemail_b200.so; the CPU oracle (oracle/) is only the checker."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle
+import zkemail_rs_b200 as z
+from zkemail_rs_b200 import synth
+from zkemail_rs_b200.structs import RegexInfo, RegexPattern
+from tests.util import NOW, assert_records_equal, key_pool, mixed_emails
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sha256_kernel_vs_hashlib_and_oracle(engine):
+    rng = np.random.default_rng(3)
+    lens = [0, 1, 3, 55, 56, 57, 63, 64, 65, 119, 120, 127, 128, 129, 4096, 4097, 520, 1000, 102400]
+    lens += [int(x) for x in rng.integers(0, 3000, size=500)]
+    msgs = [rng.integers(0, 256, size=l, dtype=np.uint8).tobytes() for l in lens]
+    msgs[1] = b"a"
+    msgs.append(b"abc")  # FIPS 180-4 KAT
+    got = engine.sha256_batch(msgs)
+    assert got[-1].hex() == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"
+    for m, g in zip(msgs, got):
+        assert g == hashlib.sha256(m).digest()
+        assert g == oracle.sha256(m)
+
+
+@pytest.mark.parametrize("lanes", [4, 8, 16])
+def test_rsa_kernel_vs_oracle(lanes):
+    from cryptography.hazmat.primitives import hashes
+    from cryptography.hazmat.primitives.asymmetric import padding
+    eng = z.Engine(rsa_lanes=lanes)
+    try:
+        rng = np.random.default_rng(5)
+        keys = key_pool()
+        ks, ds, ss = [], [], []
+        for i in range(96):
+            bits = 1024 if i % 3 == 2 else 2048
+            k = keys[bits][i % len(keys[bits])]
+            m = b"message %d" % i
+            sig = k.private.sign(m, padding.PKCS1v15(), hashes.SHA256())
+            d = hashlib.sha256(m).digest()
+            kind = i % 8
+            if kind == 1:
+                sig = bytes([sig[0] ^ 0x01]) + sig[1:]
+            elif kind == 2:
+                d = hashlib.sha256(m + b"!").digest()
+            elif kind == 3:
+                sig = sig[1:]                      # wrong length
+            elif kind == 4:
+                sig = b"\xff" * len(sig)           # s >= n
+            elif kind == 5:
+                sig = b"\x00" * len(sig)           # s = 0
+            elif kind == 6:
+                k = keys[bits][(i + 1) % len(keys[bits])]  # wrong key
+            ks.append(k.der); ds.append(d); ss.append(sig)
+        got = eng.rsa_verify_batch(ks, ds, ss)
+        exp = [oracle.rsa_verify_sha256(k, d, s) for k, d, s in zip(ks, ds, ss)]
+        assert got == exp
+        assert sum(got) >= 24
+        # key rejected by the loader
+        assert eng.rsa_verify_batch([b"\x30\x03\x02\x01\x01"], [b"\0" * 32], [b"\1"]) == [2]
+    finally:
+        eng.close()
+
+
+PATTERNS = [r"abc", r"a+", r"a*", r"(a|ab)(c|bcd)", r"from:[^\r\n]*@example\.com", r"subject:[^\r\n]+",
+            r"Transaction ID: [A-Z0-9]+", r"(?i)hello", r"a{2,4}", r"^abc", r"abc$", r"(?m)^a+$", r".*",
+            r"[^a]+", r"(foo|foobar|fo)", r"\d+\.\d+", r"to:[^\r\n]+\r\n"]
+
+
+@pytest.mark.parametrize("qp", [False, True])
+def test_dfa_kernel_vs_oracle(engine, qp):
+    rng = np.random.default_rng(11)
+    alpha = b"abcdxy @.:\r\nAB019kK=\x00"
+    hays = [b"", b"a", b"abc", b"aaab", b"xabcabcx", b"from:bob <bob@example.com>\r\nsubject:hi there\r\nto:x\r\n",
+            b"Transaction ID: A1B2C3 ok", b"hello HELLO", b"ab\nabc\naa\n", b"3.14 and 2.71", b"=\r\n", b"a=\r\nbc=\r\n"]
+    for _ in range(300):
+        l = int(rng.integers(0, 200))
+        hays.append(bytes(alpha[i] for i in rng.integers(0, len(alpha), size=l)))
+    if qp:
+        hays = [h.replace(b"b", b"b=\r\n", 1) if i % 2 else h + b"=\r\n" for i, h in enumerate(hays)]
+    for pat in PATTERNS:
+        dfa = z.compile_regex(pat)
+        got = engine.dfa_scan_batch(dfa, hays, qp=qp)
+        for h, r in zip(hays, got):
+            hay = oracle.qp_clean(h)[0] if qp else h
+            cnt, spans = oracle.dfa_find_iter(dfa.fwd, dfa.bwd, hay, 4)
+            assert int(r[0]) == cnt, (pat, h, r, cnt, spans)
+            if cnt:
+                assert (int(r[1]), int(r[2])) == spans[0], (pat, h, r, spans)
+
+
+def test_verify_batch_vs_oracle(engine):
+    emails, labels = mixed_emails(seed=21)
+    got = engine.verify_batch(emails)
+    exp = oracle.verify_batch(emails, now=NOW)
+    assert len(got) == len(exp)
+    for g, e, lab in zip(got, exp, labels):
+        assert_records_equal(g, e, lab)
+    st = [int(g["status"]) for g in got]
+    assert st.count(0) == labels.count("pos")
+    assert all(s != 0 for s, lab in zip(st, labels) if lab != "pos")
+
+
+def test_verify_with_regex_vs_oracle(engine):
+    emails, labels = mixed_emails(seed=22, with_token=True)
+    # compile against the first email's haystacks (helpers/src/generator.rs:63-78)
+    hdr, body = oracle.canonicalize_signed_email(emails[0].raw_email, NOW)
+    clean, _ = oracle.qp_clean(body)
+    header_parts = z.compile_regex_parts([RegexPattern(r"from:[^\r\n]*@mail[0-9]\.example\.com", None),
+                                          RegexPattern(r"\r\nsubject:([^\r\n]+)\r\n", None)], hdr)
+    body_parts = z.compile_regex_parts([RegexPattern(r"Transaction ID: ([A-Z0-9]+)", None)], clean)
+    for p in header_parts + body_parts:
+        p.captures = None  # per-email captures differ; checked separately below
+    info = RegexInfo(header_parts, body_parts)
+    got = engine.verify_with_regex_batch(emails, info)
+    exp = oracle.verify_batch(emails, header_parts, body_parts, now=NOW)
+    for g, e, lab in zip(got, exp, labels):
+        assert_records_equal(g, e, lab)
+    assert sum(int(g["status"]) == 0 for g in got) == labels.count("pos")
+    # captures: correct for email 0, wrong for the others -> identical verdicts on both sides
+    body_parts2 = z.compile_regex_parts([RegexPattern(r"Transaction ID: ([A-Z0-9]+)", [1])], clean)
+    info2 = RegexInfo(None, body_parts2)
+    got2 = engine.verify_with_regex_batch(emails[:6], info2)
+    exp2 = oracle.verify_batch(emails[:6], None, body_parts2, now=NOW)
+    for g, e in zip(got2, exp2):
+        assert_records_equal(g, e, "captures")
+    assert int(got2[0]["status"]) == 0 and int(got2[1]["status"]) == 7
+
+
+def test_single_email_api(engine):
+    emails, labels = mixed_emails(seed=23, n_pos=3)
+    out = engine.verify_email(emails[0])
+    assert out.from_domain_hash == hashlib.sha256(emails[0].from_domain.encode()).digest()
+    assert out.public_key_hash == hashlib.sha256(emails[0].public_key.key).digest()
+    with pytest.raises(z.VerificationPanic) as ei:
+        engine.verify_email(emails[3])  # body_flip
+    assert ei.value.status == 3
+
+
+def test_resident_batch_matches_pipeline(engine):
+    emails, labels = mixed_emails(seed=24)
+    from zkemail_rs_b200.engine import EmailViews
+    views = EmailViews.from_emails(emails)
+    a = engine.verify_views(views)
+    pb = engine.prepare(views)
+    pb.run(); pb.run()
+    b = pb.fetch()
+    st = pb.stats()
+    pb.close()
+    assert a.tobytes() == b.tobytes()
+    assert st["n_emails"] == len(emails) and st["kernel_launches"] >= 3

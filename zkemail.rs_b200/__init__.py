@@ -4,3 +4,7 @@ from .structs import (  # noqa: F401
     DFA, CompiledRegex, Email, EmailVerifierOutput, EmailWithRegex, EmailWithRegexVerifierOutput,
     ExternalInput, PublicKey, RegexConfig, RegexInfo, RegexPattern,
 )
+from .engine import (  # noqa: F401,E402
+    Engine, EngineUnavailable, RegexError, RegexSet, VerificationPanic, compile_regex,
+    canonicalize_signed_email, compile_regex_parts, verify_email, verify_email_with_regex,
+)

@@ -20,7 +20,7 @@
 //   [0..127]   n      (zero padded to 128 limbs)
 //   [128..255] R^2 mod n, R = 2^(32*limbs)
 //   [256] n0inv = -n^-1 mod 2^32   [257] e low 32   [258] e high   [259] k = byte length of n
-//   [260] limbs class (32/64/96/128)   [261..263] reserved
+//   [260] limbs class (32/64/128)   [261..263] reserved
 #define ZKB_KEY_STRIDE 264
 #define ZKB_KEY_RR 128
 #define ZKB_KEY_N0INV 256

@@ -191,16 +191,11 @@ struct Searcher {
 #define ZKB_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
 #endif
 
-// out[slot] = (match_count, first start, first end, reverse-search-failed flag)
-template <typename TT>
-__global__ void __launch_bounds__(128)
-dfa_scan_kernel(const uint8_t* __restrict__ arena, const DfaItem* __restrict__ items,
-                uint32_t n_items, const uint8_t* __restrict__ fwd_blob, uint32_t fwd_bytes,
-                const uint8_t* __restrict__ rev_blob, uint32_t rev_bytes, int use_smem, int qp,
-                uint4* __restrict__ out) {
-  ZKB_DYN_SMEM(smem);
-  const uint8_t* fb = fwd_blob;
-  const uint8_t* rb = rev_blob;
+// Copies both tables into shared memory (when they fit) and returns the pointers to scan from.
+__device__ __forceinline__ void dfa_stage_tables(uint8_t* smem, const uint8_t* __restrict__ fwd_blob, uint32_t fwd_bytes,
+                                                 const uint8_t* __restrict__ rev_blob, uint32_t rev_bytes, int use_smem,
+                                                 const uint8_t*& fb, const uint8_t*& rb) {
+  fb = fwd_blob; rb = rev_blob;
   if (use_smem) {  // blobs are 16-byte padded by the host
     uint32_t fpad = (fwd_bytes + 15u) & ~15u, rpad = (rev_bytes + 15u) & ~15u;
     for (uint32_t i = threadIdx.x * 16; i < fpad; i += blockDim.x * 16)
@@ -210,15 +205,49 @@ dfa_scan_kernel(const uint8_t* __restrict__ arena, const DfaItem* __restrict__ i
     __syncthreads();
     fb = smem; rb = smem + fpad;
   }
+}
+
+template <typename TT>
+__device__ __forceinline__ uint4 dfa_scan_one(const uint8_t* fb, const uint8_t* rb, const uint8_t* hay, uint32_t n, int qp) {
+  Searcher<TT> s;
+  s.f.init(fb); s.r.init(rb);
+  s.h = hay; s.n = n; s.qp = qp != 0;
+  uint32_t count, fs, fe; bool panic;
+  s.run(count, fs, fe, panic);
+  return make_uint4(count, fs, fe, panic ? 1u : 0u);
+}
+
+// out[slot] = (match_count, first start, first end, reverse-search-failed flag)
+template <typename TT>
+__global__ void __launch_bounds__(128)
+dfa_scan_kernel(const uint8_t* __restrict__ arena, const DfaItem* __restrict__ items,
+                uint32_t n_items, const uint8_t* __restrict__ fwd_blob, uint32_t fwd_bytes,
+                const uint8_t* __restrict__ rev_blob, uint32_t rev_bytes, int use_smem, int qp,
+                uint4* __restrict__ out) {
+  ZKB_DYN_SMEM(smem);
+  const uint8_t *fb, *rb;
+  dfa_stage_tables(smem, fwd_blob, fwd_bytes, rev_blob, rev_bytes, use_smem, fb, rb);
   uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_items) return;
   DfaItem it = items[idx];
-  Searcher<TT> s;
-  s.f.init(fb); s.r.init(rb);
-  s.h = arena + it.hay_off; s.n = it.hay_len; s.qp = qp != 0;
-  uint32_t count, fs, fe; bool panic;
-  s.run(count, fs, fe, panic);
-  out[it.out_slot] = make_uint4(count, fs, fe, panic ? 1u : 0u);
+  out[it.out_slot] = dfa_scan_one<TT>(fb, rb, arena + it.hay_off, it.hay_len, qp);
+}
+
+// Engine form: items are interleaved per email (2*j = header preimage, 2*j+1 = canonical body);
+// `which` selects the haystack, the result of regex part `pi` of P goes to out[email * P + pi].
+template <typename TT>
+__global__ void __launch_bounds__(128)
+dfa_scan_strided(const uint8_t* __restrict__ arena, const DfaItem* __restrict__ items, uint32_t n_emails,
+                 uint32_t which, uint32_t P, uint32_t pi, const uint8_t* __restrict__ fwd_blob, uint32_t fwd_bytes,
+                 const uint8_t* __restrict__ rev_blob, uint32_t rev_bytes, int use_smem, int qp,
+                 uint4* __restrict__ out) {
+  ZKB_DYN_SMEM(smem);
+  const uint8_t *fb, *rb;
+  dfa_stage_tables(smem, fwd_blob, fwd_bytes, rev_blob, rev_bytes, use_smem, fb, rb);
+  uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_emails) return;
+  DfaItem it = items[2 * idx + which];
+  out[(size_t)it.out_slot * P + pi] = dfa_scan_one<TT>(fb, rb, arena + it.hay_off, it.hay_len, qp);
 }
 
 }  // namespace zkb

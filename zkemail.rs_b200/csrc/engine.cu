@@ -1,0 +1,1401 @@
+// engine.cu — libzkemail_b200.so: the C ABI of include/zkemail_b200.h.
+//
+// Replaces the native execution of zkemail_core::verify_email (core/src/circuits.rs:9-29) and
+// verify_email_with_regex (core/src/circuits.rs:31-68) for whole batches:
+//   host  : header split, DKIM-Signature tag parsing, header selection, canonicalisation, base64
+//           (dkim_host.hpp) on a thread pool, written straight into pinned staging blocks;
+//   device: SHA-256 of every body / header preimage / from_domain / key (sha256.cuh), bh= compare,
+//           RSA PKCS#1 v1.5 verification (rsa.cuh), regex DFA scans (dfa.cuh);
+//   host  : per-email resolution of the reference's control flow (first passing signature wins,
+//           every panic site becomes a status code).
+// There is no CPU fallback for the arithmetic: without a CUDA device zkb_engine_create fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/zkemail_b200.h"
+#include "common.cuh"
+#include "dfa_host.hpp"
+#include "dkim_host.hpp"
+#include "kernels.h"
+#include "keytab.hpp"
+#include "regexc.hpp"
+
+using namespace zkb;
+
+namespace {
+
+#define CK(expr)                                                                             \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      fprintf(stderr, "[zkemail_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e),   \
+              __FILE__, __LINE__, cudaGetErrorString(_e));                                   \
+      return ZKB_E_CUDA;                                                                     \
+    }                                                                                        \
+  } while (0)
+
+// ------------------------------------------------------------------ thread pool
+class ThreadPool {
+ public:
+  explicit ThreadPool(int n) : n_(n < 1 ? 1 : n) {
+    for (int i = 1; i < n_; i++) th_.emplace_back([this, i] { worker(i); });
+  }
+  ~ThreadPool() {
+    { std::lock_guard<std::mutex> l(mu_); stop_ = true; gen_++; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  int size() const { return n_; }
+  // runs fn(tid) once on every thread of the pool (the caller is tid 0) and waits for all
+  void run(const std::function<void(int)>& fn) {
+    { std::lock_guard<std::mutex> l(mu_); job_ = &fn; pending_ = n_ - 1; gen_++; }
+    cv_.notify_all();
+    fn(0);
+    std::unique_lock<std::mutex> l(mu_);
+    done_.wait(l, [this] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+  // dynamic parallel-for over [0,n) in grains
+  void parallel_for(size_t n, size_t grain, const std::function<void(size_t, size_t, int)>& body) {
+    if (n == 0) return;
+    std::atomic<size_t> next{0};
+    run([&](int tid) {
+      for (;;) {
+        size_t lo = next.fetch_add(grain);
+        if (lo >= n) break;
+        body(lo, std::min(n, lo + grain), tid);
+      }
+    });
+  }
+
+ private:
+  void worker(int tid) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(int)>* job;
+      {
+        std::unique_lock<std::mutex> l(mu_);
+        cv_.wait(l, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        job = job_;
+      }
+      if (job) (*job)(tid);
+      { std::lock_guard<std::mutex> l(mu_); pending_--; }
+      done_.notify_one();
+    }
+  }
+  int n_;
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* job_ = nullptr;
+  uint64_t gen_ = 0;
+  int pending_ = 0;
+  bool stop_ = false;
+};
+
+// ------------------------------------------------------------------ pinned staging blocks
+struct PinBlock {
+  uint8_t* p = nullptr;
+  size_t cap = 0, used = 0;
+  uint64_t dev_off = 0;  // where this block's bytes live in the chunk's device arena
+};
+class BlockPool {
+ public:
+  static constexpr size_t kBlock = 8u << 20;
+  bool get(size_t min_cap, PinBlock& b) {
+    size_t want = std::max(min_cap, kBlock);
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      for (size_t i = 0; i < free_.size(); i++)
+        if (free_[i].cap >= want && (want > kBlock || free_[i].cap == kBlock)) {
+          b = free_[i]; free_[i] = free_.back(); free_.pop_back();
+          b.used = 0;
+          return true;
+        }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) return false;
+    b.p = (uint8_t*)p; b.cap = want; b.used = 0; b.dev_off = 0;
+    return true;
+  }
+  void put(PinBlock& b) {
+    if (!b.p) return;
+    std::lock_guard<std::mutex> l(mu_);
+    free_.push_back(b);
+    b = PinBlock();
+  }
+  void release_all() {
+    std::lock_guard<std::mutex> l(mu_);
+    for (auto& b : free_) cudaFreeHost(b.p);
+    free_.clear();
+  }
+ private:
+  std::mutex mu_;
+  std::vector<PinBlock> free_;
+};
+
+struct PinBuf {  // growable pinned buffer
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+  bool ensure(size_t n) {
+    if (n <= cap) return true;
+    if (p) cudaFreeHost(p);
+    size_t want = std::max(n + n / 4, (size_t)1 << 16);
+    void* q = nullptr;
+    if (cudaHostAlloc(&q, want, cudaHostAllocDefault) != cudaSuccess) { p = nullptr; cap = 0; return false; }
+    p = (uint8_t*)q; cap = want;
+    return true;
+  }
+  void free() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+struct DevBuf {  // growable device buffer
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+  bool ensure(size_t n) {
+    if (n <= cap) return true;
+    if (p) cudaFree(p);
+    size_t want = std::max(n + n / 4, (size_t)1 << 16);
+    void* q = nullptr;
+    if (cudaMalloc(&q, want) != cudaSuccess) { p = nullptr; cap = 0; return false; }
+    p = (uint8_t*)q; cap = want;
+    return true;
+  }
+  void free() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// ------------------------------------------------------------------ records produced by the host pass
+struct MsgRec {         // one SHA-256 message / DFA haystack
+  uint64_t goff;        // byte offset in the device arena (after layout)
+  uint32_t len, blk, local;
+};
+enum { SIG_OK = 0, SIG_SYNTAX = 1, SIG_BADLEN = 2 };
+struct CandRec {        // one DKIM-Signature header that reaches the cryptographic checks
+  uint32_t body_msg, hdr_msg;  // thread-local message indices
+  uint32_t bh[8];              // decoded bh= as native SHA-256 state words
+  uint32_t sig_off;            // word offset into the thread's signature words
+  int32_t key_id;
+  uint8_t bh_valid, sig_state, algo, haystack_only;
+};
+enum { STEP_ERR = 0, STEP_CAND = 1, STEP_SHA1 = 2 };
+struct StepRec { uint32_t cand; uint8_t kind, detail; };
+struct EmailRec {
+  int32_t status = 0;
+  uint32_t tid = 0, first_step = 0, n_steps = 0;
+  uint32_t dom_msg = 0, key_msg = 0;
+  int32_t canon_rc = 2;     // zo_canonicalize_signed_email return code equivalent
+  uint32_t canon_cand = 0;  // thread-local candidate whose messages are the regex haystacks
+};
+struct KeyMeta { uint32_t limbs_class = 0, k = 0; bool generic = false; };
+
+struct ThreadRecs {
+  std::vector<PinBlock> blocks;
+  std::vector<MsgRec> msgs;
+  std::vector<CandRec> cands;
+  std::vector<StepRec> steps;
+  std::vector<uint32_t> sigw;
+  uint32_t msg_base = 0, cand_base = 0;
+  void clear() { msgs.clear(); cands.clear(); steps.clear(); sigw.clear(); }
+};
+
+struct DeviceChunk {   // everything one chunk needs in HBM
+  DevBuf arena, meta, out;
+  // pointers into meta / out
+  const uint64_t* msg_off = nullptr; const uint32_t* msg_len = nullptr; const uint32_t* order = nullptr;
+  const uint32_t* cand_body = nullptr; const uint32_t* cand_bh = nullptr;
+  const uint32_t* sig_arena = nullptr;
+  const RsaItem* rsa_items[6] = {nullptr}; uint32_t rsa_n[6] = {0};  // [class 32,64,128] x [e=65537, generic]
+  const DfaItem* dfa_items = nullptr; uint32_t n_dfa = 0;
+  uint32_t* digests = nullptr; uint32_t* cand_flags = nullptr; uint4* dfa_out = nullptr;
+  uint32_t M = 0, C = 0, NE = 0, P = 0;
+  size_t out_bytes = 0;
+  void free() { arena.free(); meta.free(); out.free(); }
+};
+
+struct Chunk {  // host view of one chunk
+  size_t e0 = 0, ne = 0;
+  std::vector<EmailRec> emails;
+  std::vector<ThreadRecs> tr;
+  std::vector<uint8_t> meta_host;  // staged in pageable memory, copied through the slot's pinned meta
+  zkb_batch_stats st;
+  size_t arena_bytes = 0, meta_bytes = 0;
+  uint32_t M = 0, C = 0;
+  // offsets inside meta
+  size_t o_msg_off = 0, o_msg_len = 0, o_order = 0, o_cand_body = 0, o_cand_bh = 0, o_sig = 0, o_rsa[6] = {0}, o_dfa = 0;
+  uint32_t rsa_n[6] = {0}, n_dfa = 0;
+};
+
+struct Slot {
+  DeviceChunk dev;
+  PinBuf meta, result;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+};
+
+}  // namespace
+
+struct zkb_regex_set {
+  zkb_engine* eng = nullptr;
+  size_t n_header = 0, n_body = 0;
+  int header_present = 0, body_present = 0;
+  struct Part { uint8_t* d_fwd = nullptr; uint8_t* d_rev = nullptr; uint32_t fwd_bytes = 0, rev_bytes = 0, elem = 2; bool body = false; };
+  std::vector<Part> parts;
+  size_t n_active() const { return (header_present ? n_header : 0) + (body_present ? n_body : 0); }
+};
+
+struct zkb_engine {
+  int device = 0, sm_count = 148;
+  size_t smem_optin = 0;
+  int64_t now_unix = 0;
+  size_t chunk_emails = 32768;
+  uint32_t rsa_lanes = 8;
+  ThreadPool* pool = nullptr;
+  BlockPool blocks;
+  Slot slots[3];
+  std::mutex run_mu;
+  // public keys
+  std::mutex key_mu;
+  std::unordered_map<std::string, int32_t> key_index;
+  std::vector<uint32_t> keytab_host;
+  std::vector<KeyMeta> key_meta;
+  uint32_t* d_keytab = nullptr;
+  size_t d_keytab_cap = 0, d_keytab_n = 0;
+  cudaEvent_t ev[8] = {nullptr};
+};
+
+struct zkb_batch {
+  zkb_engine* eng = nullptr;
+  const zkb_regex_set* regex = nullptr;
+  size_t n = 0;
+  std::vector<Chunk*> chunks;
+  std::vector<DeviceChunk*> dev;
+  const zkb_email_view* emails = nullptr;       // borrowed until fetch
+  const zkb_email_captures* captures = nullptr;  // borrowed until fetch
+  float last_ms[5] = {0, 0, 0, 0, 0};
+  bool ran = false;
+};
+
+namespace {
+
+// ------------------------------------------------------------------ per-thread parse context
+struct ThreadCtx {
+  zkb_engine* eng;
+  ThreadRecs* tr;
+  std::vector<HeaderField> hs;
+  DkimSig sig;
+  std::string scratch;
+  std::vector<uint8_t> tmp;
+  std::unordered_map<std::string, std::pair<int32_t, KeyMeta>> key_cache;
+  std::unordered_map<std::string, uint32_t> dom_msgs;
+  std::unordered_map<int32_t, uint32_t> key_msgs;
+  std::string last_dom; uint32_t last_dom_msg = 0; bool have_last_dom = false;
+  bool oom = false;
+
+  // reserve `need` bytes (64-byte aligned start) in the thread's current staging block
+  uint8_t* reserve(size_t need, uint32_t& blk, uint32_t& local) {
+    if (tr->blocks.empty() || tr->blocks.back().used + need > tr->blocks.back().cap) {
+      PinBlock b;
+      if (!eng->blocks.get(need, b)) { oom = true; return nullptr; }
+      tr->blocks.push_back(b);
+    }
+    PinBlock& b = tr->blocks.back();
+    blk = (uint32_t)tr->blocks.size() - 1;
+    local = (uint32_t)b.used;
+    return b.p + b.used;
+  }
+  // commit a message of `len` bytes written at the reserved position
+  uint32_t commit(uint32_t blk, uint32_t local, size_t len) {
+    PinBlock& b = tr->blocks[blk];
+    b.used = local + (((len >> 6) + 1) << 6);  // readable up to the block after the last full one
+    MsgRec m;
+    m.goff = 0; m.len = (uint32_t)len; m.blk = blk; m.local = local;
+    tr->msgs.push_back(m);
+    return (uint32_t)tr->msgs.size() - 1;
+  }
+  uint32_t add_msg(const uint8_t* data, size_t len) {
+    uint32_t blk, local;
+    uint8_t* p = reserve(((len >> 6) + 1) << 6, blk, local);
+    if (!p) return 0;
+    if (len) memcpy(p, data, len);
+    return commit(blk, local, len);
+  }
+};
+
+int32_t lookup_key(ThreadCtx& c, const uint8_t* der, size_t len, KeyMeta& meta) {
+  std::string k((const char*)der, len);
+  auto it = c.key_cache.find(k);
+  if (it != c.key_cache.end()) { meta = it->second.second; return it->second.first; }
+  zkb_engine* e = c.eng;
+  int32_t id;
+  meta = KeyMeta();
+  {
+    std::lock_guard<std::mutex> l(e->key_mu);
+    auto g = e->key_index.find(k);
+    if (g != e->key_index.end()) id = g->second;
+    else {
+      RsaKeyInfo info;
+      if (!parse_rsa_public_key(der, len, info)) id = -1;
+      else {
+        id = (int32_t)e->key_meta.size();
+        e->keytab_host.resize((size_t)(id + 1) * ZKB_KEY_STRIDE);
+        build_key_entry(info, e->keytab_host.data() + (size_t)id * ZKB_KEY_STRIDE);
+        KeyMeta m;
+        m.limbs_class = info.limbs_class; m.k = info.k; m.generic = info.e != 65537;
+        e->key_meta.push_back(m);
+      }
+      e->key_index.emplace(k, id);
+    }
+    if (id >= 0) meta = e->key_meta[id];
+  }
+  c.key_cache.emplace(std::move(k), std::make_pair(id, meta));
+  return id;
+}
+
+// Host pass over one email: everything of verify_dkim / canonicalize_signed_email that is byte
+// shuffling.  Mirrors the control flow of cfdkim::verify_email_with_key.
+void process_email(ThreadCtx& c, const zkb_email_view& em, bool want_regex, int tid, EmailRec& rec) {
+  rec = EmailRec();
+  rec.tid = (uint32_t)tid;
+  rec.first_step = (uint32_t)c.tr->steps.size();
+  const uint8_t* raw = em.raw_email;
+  const size_t n = em.raw_email_len;
+  size_t body_off = 0;
+  if (n > 0xFFFFFF00u || !parse_headers(raw, n, c.hs, body_off)) { rec.status = ZKB_ST_MAIL_PARSE; return; }
+  int32_t key_id = -1;
+  KeyMeta km = KeyMeta();
+  if (em.key_type_len == 3 && memcmp(em.key_type, "rsa", 3) == 0) {
+    key_id = lookup_key(c, em.key, em.key_len, km);
+    if (key_id < 0) { rec.status = ZKB_ST_KEY; return; }
+  } else if (em.key_type_len == 7 && memcmp(em.key_type, "ed25519", 7) == 0) {
+    rec.status = em.key_len == 32 ? ZKB_ST_UNSUPPORTED : ZKB_ST_KEY;
+    return;
+  } else { rec.status = ZKB_ST_KEY; return; }
+
+  size_t body_len = 0;
+  const uint8_t* body = nullptr;
+  bool body_found = false;
+  struct BodyKey { bool relaxed, has_l; uint64_t l; uint32_t msg; };
+  BodyKey bodies[4];
+  int n_bodies = 0;
+  auto body_msg_for = [&](bool relaxed, bool has_l, uint64_t l) -> uint32_t {
+    for (int i = 0; i < n_bodies; i++)
+      if (bodies[i].relaxed == relaxed && bodies[i].has_l == has_l && bodies[i].l == l) return bodies[i].msg;
+    if (!body_found) { body = find_body(raw, n, body_len); body_found = true; }
+    uint32_t blk, local;
+    uint8_t* p = c.reserve((((body_len + 2) >> 6) + 1) << 6, blk, local);
+    if (!p) return 0;
+    size_t cl = relaxed ? canon_body_relaxed(body, body_len, p) : canon_body_simple(body, body_len, p);
+    if (has_l && l < cl) cl = (size_t)l;
+    uint32_t m = c.commit(blk, local, cl);
+    if (n_bodies < 4) { bodies[n_bodies].relaxed = relaxed; bodies[n_bodies].has_l = has_l; bodies[n_bodies].l = l; bodies[n_bodies].msg = m; n_bodies++; }
+    return m;
+  };
+  // builds the candidate for the signature currently held in c.sig
+  auto make_cand = [&](bool hr, bool br, bool has_l, uint64_t l, uint8_t algo, bool haystack_only) -> uint32_t {
+    CandRec cd;
+    memset(&cd, 0, sizeof cd);
+    cd.key_id = key_id; cd.algo = algo; cd.haystack_only = haystack_only ? 1 : 0;
+    cd.body_msg = body_msg_for(br, has_l, l);
+    uint32_t blk, local;
+    size_t bound = preimage_bound(body_off, c.sig.n);
+    uint8_t* p = c.reserve(((bound >> 6) + 1) << 6, blk, local);
+    if (!p) return 0;
+    size_t pl = build_header_preimage(raw, c.hs, c.sig, hr, p, c.scratch);
+    cd.hdr_msg = c.commit(blk, local, pl);
+    if (!haystack_only) {
+      const Tag* tbh = c.sig.get("bh");
+      uint8_t bh[48];
+      if (tbh->val_len == 44 && base64_decode(c.sig.val(tbh), 44, bh) == 32) {
+        cd.bh_valid = 1;
+        for (int i = 0; i < 8; i++)
+          cd.bh[i] = ((uint32_t)bh[4 * i] << 24) | ((uint32_t)bh[4 * i + 1] << 16) | ((uint32_t)bh[4 * i + 2] << 8) | bh[4 * i + 3];
+      }
+      const Tag* tb = c.sig.get("b");
+      c.tmp.resize(tb->val_len + 4);
+      long sl = base64_decode(c.sig.val(tb), tb->val_len, c.tmp.data());
+      if (sl < 0) cd.sig_state = SIG_SYNTAX;
+      else if ((size_t)sl != km.k) cd.sig_state = SIG_BADLEN;
+      else if (algo == 1) {
+        cd.sig_state = SIG_OK;
+        cd.sig_off = (uint32_t)c.tr->sigw.size();
+        c.tr->sigw.resize(c.tr->sigw.size() + km.limbs_class, 0u);
+        uint32_t* w = c.tr->sigw.data() + cd.sig_off;
+        for (long i = 0; i < sl; i++) {
+          long bi = sl - 1 - i;
+          w[bi >> 2] |= (uint32_t)c.tmp[i] << (8 * (bi & 3));
+        }
+      }
+    }
+    c.tr->cands.push_back(cd);
+    return (uint32_t)c.tr->cands.size() - 1;
+  };
+
+  bool canon_seen = false;
+  for (size_t hi = 0; hi < c.hs.size(); hi++) {
+    const HeaderField& h = c.hs[hi];
+    if (!ieq_ascii(raw + h.key_off, h.key_len, "DKIM-Signature", 14)) continue;
+    int r = validate_dkim_header(raw + h.val_off, h.val_len, c.eng->now_unix, c.sig);
+    if (r != ZKB_DKIM_PASS) {
+      StepRec s; s.kind = STEP_ERR; s.detail = (uint8_t)r; s.cand = 0;
+      c.tr->steps.push_back(s);
+      continue;
+    }
+    // this header is the one canonicalize_signed_email would use if it is the first valid one
+    const bool is_canon = want_regex && !canon_seen;
+    canon_seen = true;
+    bool hr = false, br = false;
+    const bool canon_ok = parse_canon_tag(c.sig, hr, br);
+    uint64_t lval = 0;
+    bool has_l = false, l_ok = true;
+    if (const Tag* tl = c.sig.get("l")) { has_l = true; l_ok = parse_usize_tag(c.sig, tl, lval); }
+    long verify_cand = -1;
+    {
+      const Tag* td = c.sig.get("d");
+      StepRec s; s.cand = 0; s.detail = 0;
+      bool push = true;
+      if (!ieq_ascii(c.sig.val(td), td->val_len, em.from_domain, em.from_domain_len)) push = false;  // skipped, not an error
+      else if (!canon_ok) { s.kind = STEP_ERR; s.detail = ZKB_DKIM_CANON_TYPE; }
+      else {
+        const Tag* ta = c.sig.get("a");
+        int algo = c.sig.val_is(ta, "rsa-sha1") ? 0 : c.sig.val_is(ta, "rsa-sha256") ? 1 : c.sig.val_is(ta, "ed25519-sha256") ? 2 : -1;
+        if (algo < 0) { s.kind = STEP_ERR; s.detail = ZKB_DKIM_HASH_ALGO; }
+        else if (algo == 0) { s.kind = STEP_SHA1; }
+        else if (!l_ok) { s.kind = STEP_ERR; s.detail = ZKB_DKIM_LENGTH_TAG; }
+        else {
+          verify_cand = (long)make_cand(hr, br, has_l, lval, (uint8_t)algo, false);
+          s.kind = STEP_CAND; s.cand = (uint32_t)verify_cand;
+        }
+      }
+      if (push) c.tr->steps.push_back(s);
+    }
+    if (is_canon) {
+      if (!canon_ok) rec.canon_rc = 3;
+      else if (!l_ok) rec.canon_rc = 4;
+      else {
+        const Tag* tb = c.sig.get("b");
+        c.tmp.resize(tb->val_len + 4);
+        if (base64_decode(c.sig.val(tb), tb->val_len, c.tmp.data()) < 0) rec.canon_rc = 5;
+        else {
+          rec.canon_rc = 0;
+          rec.canon_cand = verify_cand >= 0 ? (uint32_t)verify_cand : make_cand(hr, br, has_l, lval, 1, true);
+        }
+      }
+    }
+  }
+  rec.n_steps = (uint32_t)c.tr->steps.size() - rec.first_step;
+  // from_domain / key hashes (circuits.rs:16-17), one message per distinct value and thread
+  if (c.have_last_dom && c.last_dom.size() == em.from_domain_len && memcmp(c.last_dom.data(), em.from_domain, em.from_domain_len) == 0) rec.dom_msg = c.last_dom_msg;
+  else {
+    std::string d(em.from_domain, em.from_domain_len);
+    auto it = c.dom_msgs.find(d);
+    if (it != c.dom_msgs.end()) rec.dom_msg = it->second;
+    else { rec.dom_msg = c.add_msg((const uint8_t*)em.from_domain, em.from_domain_len); c.dom_msgs.emplace(d, rec.dom_msg); }
+    c.last_dom.swap(d); c.last_dom_msg = rec.dom_msg; c.have_last_dom = true;
+  }
+  auto kt = c.key_msgs.find(key_id);
+  if (kt != c.key_msgs.end()) rec.key_msg = kt->second;
+  else { rec.key_msg = c.add_msg(em.key, em.key_len); c.key_msgs.emplace(key_id, rec.key_msg); }
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int rsa_list_of(const KeyMeta& k) { return (k.limbs_class == 32 ? 0 : k.limbs_class == 64 ? 1 : 2) * 2 + (k.generic ? 1 : 0); }
+
+// Host pack of emails [e0, e0+ne): parallel parse + layout of the SoA meta buffers.
+int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne, const zkb_regex_set* rs, Chunk& ch) {
+  const int T = e->pool->size();
+  ch.e0 = e0; ch.ne = ne;
+  ch.emails.assign(ne, EmailRec());
+  ch.tr.resize(T);
+  for (auto& t : ch.tr) t.clear();
+  const bool want_regex = rs != nullptr;
+  std::atomic<size_t> next{0};
+  std::atomic<int> oom{0};
+  const size_t grain = std::max<size_t>(16, std::min<size_t>(512, ne / (size_t)(T * 8) + 1));
+  e->pool->run([&](int tid) {
+    ThreadCtx c;
+    c.eng = e; c.tr = &ch.tr[tid];
+    for (;;) {
+      size_t lo = next.fetch_add(grain);
+      if (lo >= ne) break;
+      size_t hi = std::min(ne, lo + grain);
+      for (size_t i = lo; i < hi; i++) {
+        process_email(c, emails[e0 + i], want_regex, tid, ch.emails[i]);
+        if (c.oom) { oom = 1; return; }
+      }
+    }
+  });
+  if (oom) return ZKB_E_NOMEM;
+  // layout: device arena = concatenation of the used parts of all staging blocks
+  uint64_t off = 0;
+  uint32_t M = 0, C = 0;
+  size_t sig_words = 0;
+  for (auto& t : ch.tr) {
+    for (auto& b : t.blocks) { b.dev_off = off; off += align_up(b.used, 128); }
+    t.msg_base = M; t.cand_base = C;
+    M += (uint32_t)t.msgs.size(); C += (uint32_t)t.cands.size();
+    sig_words += t.sigw.size();
+  }
+  ch.arena_bytes = (size_t)off + 128;
+  ch.M = M; ch.C = C;
+  // RSA lists
+  uint32_t rn[6] = {0, 0, 0, 0, 0, 0};
+  for (auto& t : ch.tr)
+    for (auto& cd : t.cands)
+      if (!cd.haystack_only && cd.sig_state == SIG_OK && cd.algo == 1) rn[rsa_list_of(e->key_meta[cd.key_id])]++;
+  const size_t P = rs ? rs->n_active() : 0;
+  uint32_t n_dfa = 0;
+  if (P) for (auto& er : ch.emails) if (er.status == ZKB_ST_OK && er.canon_rc == 0) n_dfa++;
+  ch.n_dfa = n_dfa;
+  // meta offsets
+  size_t o = 0;
+  ch.o_msg_off = o; o += align_up((size_t)M * 8, 16);
+  ch.o_msg_len = o; o += align_up((size_t)M * 4, 16);
+  ch.o_order = o; o += align_up((size_t)M * 4, 16);
+  ch.o_cand_body = o; o += align_up((size_t)C * 4, 16);
+  ch.o_cand_bh = o; o += align_up((size_t)C * 32, 16);
+  ch.o_sig = o; o += align_up(sig_words * 4, 16);
+  for (int k = 0; k < 6; k++) { ch.o_rsa[k] = o; ch.rsa_n[k] = rn[k]; o += align_up((size_t)rn[k] * sizeof(RsaItem), 16); }
+  ch.o_dfa = o; o += align_up((size_t)n_dfa * 2 * sizeof(DfaItem), 16);  // header haystack + body haystack per email
+  ch.meta_bytes = o + 16;
+  ch.meta_host.assign(ch.meta_bytes, 0);
+  uint8_t* mh = ch.meta_host.data();
+  uint64_t* msg_off = (uint64_t*)(mh + ch.o_msg_off);
+  uint32_t* msg_len = (uint32_t*)(mh + ch.o_msg_len);
+  uint32_t* order = (uint32_t*)(mh + ch.o_order);
+  uint32_t* cand_body = (uint32_t*)(mh + ch.o_cand_body);
+  uint32_t* cand_bh = (uint32_t*)(mh + ch.o_cand_bh);
+  uint32_t* sigw = (uint32_t*)(mh + ch.o_sig);
+  // per-thread slices (parallel)
+  std::vector<size_t> sig_base(T, 0);
+  { size_t s = 0; for (int t = 0; t < T; t++) { sig_base[t] = s; s += ch.tr[t].sigw.size(); } }
+  uint64_t sha_blocks = 0, sha_bytes = 0;
+  e->pool->run([&](int tid) {
+    ThreadRecs& t = ch.tr[tid];
+    for (size_t i = 0; i < t.msgs.size(); i++) {
+      MsgRec& m = t.msgs[i];
+      m.goff = t.blocks[m.blk].dev_off + m.local;
+      msg_off[t.msg_base + i] = m.goff;
+      msg_len[t.msg_base + i] = m.len;
+    }
+    for (size_t i = 0; i < t.cands.size(); i++) {
+      const CandRec& cd = t.cands[i];
+      cand_body[t.cand_base + i] = t.msg_base + cd.body_msg;
+      memcpy(cand_bh + (size_t)(t.cand_base + i) * 8, cd.bh, 32);
+    }
+    if (!t.sigw.empty()) memcpy(sigw + sig_base[tid], t.sigw.data(), t.sigw.size() * 4);
+  });
+  // message order: descending block count (counting sort), keeps the lanes of a warp converged
+  {
+    uint32_t maxb = 0;
+    std::vector<uint32_t> nb(M);
+    for (uint32_t i = 0; i < M; i++) {
+      uint32_t len = msg_len[i];
+      uint32_t b = (len >> 6) + 1 + ((len & 63) >= 56 ? 1 : 0);
+      nb[i] = b; maxb = std::max(maxb, b);
+      sha_blocks += b; sha_bytes += len;
+    }
+    std::vector<uint32_t> cnt((size_t)maxb + 2, 0);
+    for (uint32_t i = 0; i < M; i++) cnt[maxb - nb[i]]++;
+    uint32_t acc = 0;
+    for (size_t b = 0; b <= maxb; b++) { uint32_t c = cnt[b]; cnt[b] = acc; acc += c; }
+    for (uint32_t i = 0; i < M; i++) order[cnt[maxb - nb[i]]++] = i;
+  }
+  // RSA items
+  {
+    uint32_t fill[6] = {0, 0, 0, 0, 0, 0};
+    for (int tid = 0; tid < T; tid++) {
+      ThreadRecs& t = ch.tr[tid];
+      for (size_t i = 0; i < t.cands.size(); i++) {
+        const CandRec& cd = t.cands[i];
+        if (cd.haystack_only || cd.sig_state != SIG_OK || cd.algo != 1) continue;
+        const KeyMeta& km = e->key_meta[cd.key_id];
+        int k = rsa_list_of(km);
+        RsaItem* items = (RsaItem*)(mh + ch.o_rsa[k]);
+        RsaItem it;
+        it.sig_off = (uint32_t)(sig_base[tid] + cd.sig_off);
+        it.key_id = (uint32_t)cd.key_id;
+        it.digest_slot = t.msg_base + cd.hdr_msg;
+        it.cand = t.cand_base + (uint32_t)i;
+        items[fill[k]++] = it;
+      }
+    }
+  }
+  // DFA items: for each email with haystacks, slot 2*j = header preimage, 2*j+1 = canonical body
+  uint64_t dfa_bytes = 0;
+  if (P) {
+    DfaItem* items = (DfaItem*)(mh + ch.o_dfa);
+    uint32_t j = 0;
+    for (size_t i = 0; i < ne; i++) {
+      EmailRec& er = ch.emails[i];
+      if (er.status != ZKB_ST_OK || er.canon_rc != 0) continue;
+      ThreadRecs& t = ch.tr[er.tid];
+      const CandRec& cd = t.cands[er.canon_cand];
+      const MsgRec& hm = t.msgs[cd.hdr_msg];
+      const MsgRec& bm = t.msgs[cd.body_msg];
+      items[2 * j].hay_off = hm.goff; items[2 * j].hay_len = hm.len; items[2 * j].out_slot = (uint32_t)i;
+      items[2 * j + 1].hay_off = bm.goff; items[2 * j + 1].hay_len = bm.len; items[2 * j + 1].out_slot = (uint32_t)i;
+      dfa_bytes += (uint64_t)hm.len * (rs->header_present ? rs->n_header : 0) + (uint64_t)bm.len * (rs->body_present ? rs->n_body : 0);
+      j++;
+    }
+  }
+  memset(&ch.st, 0, sizeof ch.st);
+  ch.st.n_emails = ne; ch.st.n_candidates = C; ch.st.n_sha_messages = M;
+  ch.st.sha_blocks = sha_blocks; ch.st.sha_bytes = sha_bytes;
+  ch.st.rsa_items_1024 = rn[0] + rn[1]; ch.st.rsa_items_2048 = rn[2] + rn[3]; ch.st.rsa_items_other = rn[4] + rn[5];
+  {
+    uint64_t macs = 0;
+    for (int k = 0; k < 6; k++) { uint64_t l = k < 2 ? 32 : k < 4 ? 64 : 128; macs += (uint64_t)rn[k] * 18ull * (2 * l * l + l); }
+    ch.st.rsa_macs = macs;
+  }
+  ch.st.dfa_items = (uint64_t)n_dfa * P; ch.st.dfa_bytes = dfa_bytes;
+  ch.st.arena_bytes = ch.arena_bytes;
+  ch.st.h2d_bytes = off + ch.meta_bytes;
+  return ZKB_OK;
+}
+
+size_t out_layout(uint32_t M, uint32_t C, size_t ne, size_t P, size_t& o_flags, size_t& o_dfa) {
+  size_t o = align_up((size_t)M * 32, 16);
+  o_flags = o; o += align_up((size_t)C * 4, 16);
+  o_dfa = o; o += ne * P * 16;
+  return o + 16;
+}
+
+// Device buffers + H2D of one packed chunk on `stream`.
+int upload_chunk(zkb_engine* e, Chunk& ch, const zkb_regex_set* rs, DeviceChunk& d, PinBuf& pin_meta, cudaStream_t stream) {
+  const size_t P = rs ? rs->n_active() : 0;
+  if (!d.arena.ensure(ch.arena_bytes) || !d.meta.ensure(ch.meta_bytes)) return ZKB_E_NOMEM;
+  size_t o_flags, o_dfa;
+  d.out_bytes = out_layout(ch.M, ch.C, ch.ne, P, o_flags, o_dfa);
+  if (!d.out.ensure(d.out_bytes)) return ZKB_E_NOMEM;
+  if (!pin_meta.ensure(ch.meta_bytes)) return ZKB_E_NOMEM;
+  memcpy(pin_meta.p, ch.meta_host.data(), ch.meta_bytes);
+  for (auto& t : ch.tr)
+    for (auto& b : t.blocks)
+      if (b.used) CK(cudaMemcpyAsync(d.arena.p + b.dev_off, b.p, b.used, cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(d.meta.p, pin_meta.p, ch.meta_bytes, cudaMemcpyHostToDevice, stream));
+  CK(cudaMemsetAsync(d.out.p + o_flags, 0, align_up((size_t)ch.C * 4, 16), stream));
+  if (P) CK(cudaMemsetAsync(d.out.p + o_dfa, 0, ch.ne * P * 16, stream));
+  d.msg_off = (const uint64_t*)(d.meta.p + ch.o_msg_off);
+  d.msg_len = (const uint32_t*)(d.meta.p + ch.o_msg_len);
+  d.order = (const uint32_t*)(d.meta.p + ch.o_order);
+  d.cand_body = (const uint32_t*)(d.meta.p + ch.o_cand_body);
+  d.cand_bh = (const uint32_t*)(d.meta.p + ch.o_cand_bh);
+  d.sig_arena = (const uint32_t*)(d.meta.p + ch.o_sig);
+  for (int k = 0; k < 6; k++) { d.rsa_items[k] = (const RsaItem*)(d.meta.p + ch.o_rsa[k]); d.rsa_n[k] = ch.rsa_n[k]; }
+  d.dfa_items = (const DfaItem*)(d.meta.p + ch.o_dfa); d.n_dfa = ch.n_dfa;
+  d.digests = (uint32_t*)d.out.p;
+  d.cand_flags = (uint32_t*)(d.out.p + o_flags);
+  d.dfa_out = (uint4*)(d.out.p + o_dfa);
+  d.M = ch.M; d.C = ch.C; d.NE = (uint32_t)ch.ne; d.P = (uint32_t)P;
+  return ZKB_OK;
+}
+
+int sync_keytab(zkb_engine* e, cudaStream_t stream) {
+  std::lock_guard<std::mutex> l(e->key_mu);
+  size_t nkeys = e->key_meta.size();
+  if (nkeys == e->d_keytab_n) return ZKB_OK;
+  if (nkeys > e->d_keytab_cap) {
+    CK(cudaStreamSynchronize(stream));
+    for (auto& s : e->slots) if (s.stream) CK(cudaStreamSynchronize(s.stream));
+    if (e->d_keytab) cudaFree(e->d_keytab);
+    size_t cap = std::max<size_t>(1024, nkeys * 2);
+    CK(cudaMalloc((void**)&e->d_keytab, cap * ZKB_KEY_STRIDE * 4));
+    e->d_keytab_cap = cap;
+    e->d_keytab_n = 0;
+  }
+  // the table is small; key ids are append-only, so re-upload the new tail synchronously
+  CK(cudaMemcpyAsync(e->d_keytab + e->d_keytab_n * ZKB_KEY_STRIDE, e->keytab_host.data() + e->d_keytab_n * ZKB_KEY_STRIDE,
+                     (nkeys - e->d_keytab_n) * ZKB_KEY_STRIDE * 4, cudaMemcpyHostToDevice, stream));
+  CK(cudaStreamSynchronize(stream));
+  e->d_keytab_n = nkeys;
+  return ZKB_OK;
+}
+
+// Enqueues every kernel of one chunk.  ev (optional): 5 events recorded around the kernel families.
+int launch_chunk(zkb_engine* e, const DeviceChunk& d, const zkb_regex_set* rs, cudaStream_t s, cudaEvent_t* ev, uint64_t* launches) {
+  uint64_t nl = 0;
+  if (ev) CK(cudaEventRecord(ev[0], s));
+  if (d.M) { launch_sha256(d.arena.p, d.msg_off, d.msg_len, d.order, d.M, d.digests, s); nl++; }
+  if (ev) CK(cudaEventRecord(ev[1], s));
+  if (d.C) { launch_bh_check(d.digests, d.cand_body, d.cand_bh, d.C, d.cand_flags, s); nl++; }
+  if (ev) CK(cudaEventRecord(ev[2], s));
+  const int lanes = (int)e->rsa_lanes;
+  for (int k = 0; k < 6; k++) {
+    if (!d.rsa_n[k]) continue;
+    const bool generic = (k & 1) != 0;
+    switch (k >> 1) {
+      case 0: launch_rsa32(generic, std::max(2, lanes / 2), d.sig_arena, d.rsa_items[k], d.rsa_n[k], e->d_keytab, d.digests, d.cand_flags, s); break;
+      case 1: launch_rsa64(generic, lanes, d.sig_arena, d.rsa_items[k], d.rsa_n[k], e->d_keytab, d.digests, d.cand_flags, s); break;
+      default: launch_rsa128(generic, std::min(16, lanes * 2), d.sig_arena, d.rsa_items[k], d.rsa_n[k], e->d_keytab, d.digests, d.cand_flags, s); break;
+    }
+    nl++;
+  }
+  if (ev) CK(cudaEventRecord(ev[3], s));
+  if (rs && d.n_dfa) {
+    size_t pi = 0;
+    for (size_t p = 0; p < rs->parts.size(); p++) {
+      const zkb_regex_set::Part& part = rs->parts[p];
+      if (part.body ? !rs->body_present : !rs->header_present) continue;
+      // items are interleaved (header, body) per email; out slot = email * P + pi
+      launch_dfa_strided(part.elem, d.arena.p, d.dfa_items, d.n_dfa, part.body ? 1u : 0u, (uint32_t)d.P, (uint32_t)pi, part.d_fwd,
+                         part.fwd_bytes, part.d_rev, part.rev_bytes, e->smem_optin, part.body ? 1 : 0, d.dfa_out, s);
+      nl++; pi++;
+    }
+  }
+  if (ev) CK(cudaEventRecord(ev[4], s));
+  CK(cudaGetLastError());
+  if (launches) *launches += nl;
+  return ZKB_OK;
+}
+
+// ------------------------------------------------------------------ result resolution (host)
+struct HayView { const uint8_t* p; uint32_t n; };
+
+// cleaned [start,end) of a haystack (soft breaks removed, zero padded) for the capture check
+void cleaned_span(const HayView& h, bool qp, uint32_t start, uint32_t end, std::string& out) {
+  out.clear();
+  if (!qp) { if (end <= h.n && start <= end) out.assign((const char*)h.p + start, end - start); return; }
+  uint32_t c = 0, o = 0;
+  while (c < end) {
+    while (o + 2 < h.n && h.p[o] == '=' && h.p[o + 1] == '\r' && h.p[o + 2] == '\n') o += 3;
+    char b = 0;
+    if (o < h.n) b = (char)h.p[o++];
+    if (c >= start) out.push_back(b);
+    c++;
+  }
+}
+
+void resolve_email(const zkb_engine* e, const Chunk& ch, size_t i, const uint8_t* outp, size_t o_flags, size_t o_dfa,
+                   const zkb_regex_set* rs, const zkb_email_captures* caps, const std::function<HayView(const ThreadRecs&, const MsgRec&)>& hay,
+                   zkb_result& res, std::string& s1, std::string& s2) {
+  memset(&res, 0, sizeof res);
+  res.dkim_detail = ZKB_DKIM_NEUTRAL;
+  const EmailRec& er = ch.emails[i];
+  if (er.status != ZKB_ST_OK) { res.status = er.status; return; }
+  const ThreadRecs& t = ch.tr[er.tid];
+  const uint32_t* digests = (const uint32_t*)outp;
+  const uint32_t* flags = (const uint32_t*)(outp + o_flags);
+  auto put_digest = [&](uint8_t* dst, uint32_t gmsg) {
+    const uint32_t* w = digests + (size_t)gmsg * 8;
+    for (int k = 0; k < 8; k++) { dst[4 * k] = (uint8_t)(w[k] >> 24); dst[4 * k + 1] = (uint8_t)(w[k] >> 16); dst[4 * k + 2] = (uint8_t)(w[k] >> 8); dst[4 * k + 3] = (uint8_t)w[k]; }
+  };
+  bool have_err = false, saw_sha1 = false, pass = false;
+  int last_err = ZKB_DKIM_NEUTRAL;
+  for (uint32_t k = 0; k < er.n_steps && !pass; k++) {
+    const StepRec& st = t.steps[er.first_step + k];
+    if (st.kind == STEP_ERR) { have_err = true; last_err = st.detail; continue; }
+    if (st.kind == STEP_SHA1) { saw_sha1 = true; continue; }
+    const CandRec& cd = t.cands[st.cand];
+    const uint32_t f = flags[t.cand_base + st.cand];
+    put_digest(res.body_hash, t.msg_base + cd.body_msg);
+    put_digest(res.header_hash, t.msg_base + cd.hdr_msg);
+    res.bh_ok = (cd.bh_valid && (f & ZKB_F_BH_OK)) ? 1 : 0;
+    res.rsa_ok = 0;
+    if (!res.bh_ok) { have_err = true; last_err = ZKB_DKIM_BODY_HASH; continue; }
+    if (cd.sig_state == SIG_SYNTAX) { have_err = true; last_err = ZKB_DKIM_SIG_SYNTAX; continue; }
+    if (cd.algo == 2) { have_err = true; last_err = ZKB_DKIM_ALGO_KEY_MISMATCH; continue; }
+    if (cd.sig_state == SIG_OK && (f & ZKB_F_RSA_OK)) { res.rsa_ok = 1; pass = true; break; }
+    have_err = true; last_err = ZKB_DKIM_SIG_MISMATCH;
+  }
+  if (!pass) {
+    res.dkim_detail = have_err ? last_err : ZKB_DKIM_NEUTRAL;
+    res.status = saw_sha1 ? ZKB_ST_UNSUPPORTED : ZKB_ST_DKIM_FAIL;
+    return;
+  }
+  res.dkim_detail = ZKB_DKIM_PASS;
+  put_digest(res.from_domain_hash, t.msg_base + er.dom_msg);
+  put_digest(res.public_key_hash, t.msg_base + er.key_msg);
+  if (!rs) return;
+  if (er.canon_rc != 0) { res.status = ZKB_ST_CANONICALIZE; return; }
+  const size_t P = rs->n_active();
+  const uint4* dfa = (const uint4*)(outp + o_dfa) + i * P;
+  const CandRec& cc = t.cands[er.canon_cand];
+  size_t pi = 0;
+  for (size_t p = 0; p < rs->parts.size(); p++) {
+    const bool body = rs->parts[p].body;
+    if (body ? !rs->body_present : !rs->header_present) continue;
+    const uint4 r = dfa[pi++];
+    uint32_t slot = res.n_parts;
+    if (slot < ZKB_MAX_PARTS) {
+      res.parts[slot].match_count = r.x; res.parts[slot].start = r.y; res.parts[slot].end = r.z; res.parts[slot].captures_ok = 0;
+      res.n_parts++;
+    }
+    bool ok = r.x == 1;
+    if (ok && caps) {
+      const zkb_email_captures& ec = caps[ch.e0 + i];
+      bool loaded = false;
+      for (size_t q = 0; q < ec.n_caps && ok; q++) {
+        if (ec.caps[q].part != p) continue;
+        if (!loaded) {
+          HayView hv = hay(t, t.msgs[body ? cc.body_msg : cc.hdr_msg]);
+          cleaned_span(hv, body, r.y, r.z, s1);
+          bool ascii = true;
+          for (char ch2 : s1) if (ch2 & 0x80) { ascii = false; break; }
+          if (!ascii) { utf8_lossy((const uint8_t*)s1.data(), s1.size(), s2); s1.swap(s2); }
+          loaded = true;
+        }
+        if (ec.caps[q].len && s1.find(ec.caps[q].s, 0, ec.caps[q].len) == std::string::npos) ok = false;
+      }
+    }
+    if (ok && slot < ZKB_MAX_PARTS) res.parts[slot].captures_ok = 1;
+    if (!ok) { res.status = body ? ZKB_ST_REGEX_BODY : ZKB_ST_REGEX_HEADER; return; }
+  }
+}
+
+void resolve_chunk(zkb_engine* e, const Chunk& ch, const uint8_t* outp, const zkb_regex_set* rs, const zkb_email_captures* caps,
+                   const std::function<HayView(const ThreadRecs&, const MsgRec&)>& hay, zkb_result* out) {
+  const size_t P = rs ? rs->n_active() : 0;
+  size_t o_flags, o_dfa;
+  out_layout(ch.M, ch.C, ch.ne, P, o_flags, o_dfa);
+  e->pool->parallel_for(ch.ne, 256, [&](size_t lo, size_t hi, int) {
+    std::string s1, s2;
+    for (size_t i = lo; i < hi; i++) resolve_email(e, ch, i, outp, o_flags, o_dfa, rs, caps, hay, out[ch.e0 + i], s1, s2);
+  });
+}
+
+void release_blocks(zkb_engine* e, Chunk& ch) {
+  for (auto& t : ch.tr) { for (auto& b : t.blocks) e->blocks.put(b); t.blocks.clear(); }
+}
+
+int ensure_dfa_attr(zkb_engine* e) {
+  CK(dfa_set_smem_limit(e->smem_optin));
+  return ZKB_OK;
+}
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+int zkb_abi_version(void) { return ZKB_ABI_VERSION; }
+
+const char* zkb_strerror(int code) {
+  switch (code) {
+    case ZKB_OK: return "ok";
+    case ZKB_E_INVALID: return "invalid argument";
+    case ZKB_E_NO_DEVICE: return "no usable CUDA device (zkemail_b200 has no CPU fallback)";
+    case ZKB_E_CUDA: return "CUDA runtime error";
+    case ZKB_E_NOMEM: return "out of memory";
+    case ZKB_E_REGEX: return "regex pattern or DFA table rejected";
+    case ZKB_E_UNSUPPORTED: return "unsupported";
+  }
+  return "unknown error";
+}
+
+int zkb_engine_create(const zkb_options* opt, zkb_engine** out) {
+  if (!out) return ZKB_E_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return ZKB_E_NO_DEVICE; }
+  int dev = opt ? opt->device : 0;
+  if (dev < 0 || dev >= ndev) return ZKB_E_INVALID;
+  CK(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 10) {
+    fprintf(stderr, "[zkemail_b200] device %d is sm_%d%d; this library carries sm_100a code only\n", dev, prop.major, prop.minor);
+    return ZKB_E_NO_DEVICE;
+  }
+  zkb_engine* e = new zkb_engine();
+  e->device = dev;
+  e->sm_count = prop.multiProcessorCount;
+  e->smem_optin = prop.sharedMemPerBlockOptin;
+  e->now_unix = opt ? opt->now_unix : 0;
+  if (opt && opt->chunk_emails) e->chunk_emails = (size_t)opt->chunk_emails;
+  if (opt && opt->rsa_lanes) e->rsa_lanes = opt->rsa_lanes;
+  int nt = opt ? opt->host_threads : 0;
+  if (nt <= 0) nt = (int)std::thread::hardware_concurrency();
+  if (nt <= 0) nt = 1;
+  if (nt > 256) nt = 256;
+  e->pool = new ThreadPool(nt);
+  for (auto& s : e->slots) {
+    CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  }
+  for (auto& ev : e->ev) CK(cudaEventCreate(&ev));
+  if (ensure_dfa_attr(e)) return ZKB_E_CUDA;
+  *out = e;
+  return ZKB_OK;
+}
+
+void zkb_engine_destroy(zkb_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (auto& s : e->slots) {
+    s.dev.free(); s.meta.free(); s.result.free();
+    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.done) cudaEventDestroy(s.done);
+  }
+  for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+  if (e->d_keytab) cudaFree(e->d_keytab);
+  e->blocks.release_all();
+  delete e->pool;
+  delete e;
+}
+
+void* zkb_engine_stream(zkb_engine* e) { return e ? (void*)e->slots[0].stream : nullptr; }
+
+int zkb_regex_set_create(zkb_engine* e, const zkb_dfa_view* parts, size_t n_header, size_t n_body, int header_present,
+                         int body_present, zkb_regex_set** out) {
+  if (!e || !out || (!parts && n_header + n_body)) return ZKB_E_INVALID;
+  *out = nullptr;
+  CK(cudaSetDevice(e->device));
+  size_t active = (header_present ? n_header : 0) + (body_present ? n_body : 0);
+  if (active > ZKB_MAX_PARTS) return ZKB_E_UNSUPPORTED;
+  zkb_regex_set* rs = new zkb_regex_set();
+  rs->eng = e; rs->n_header = n_header; rs->n_body = n_body;
+  rs->header_present = header_present; rs->body_present = body_present;
+  for (size_t p = 0; p < n_header + n_body; p++) {
+    std::vector<uint8_t> fb, rb;
+    uint32_t fe = 2, re = 2;
+    if (!build_dfa_blob(parts[p].fwd, parts[p].fwd_len, false, fb, fe) || !build_dfa_blob(parts[p].bwd, parts[p].bwd_len, true, rb, re)) {
+      zkb_regex_set_destroy(rs);
+      return ZKB_E_REGEX;
+    }
+    if (fe != re) {  // the kernel is instantiated for one element width: widen the narrow table
+      std::vector<uint8_t>& nb = fe == 2 ? fb : rb;
+      const uint32_t* h = (const uint32_t*)nb.data();
+      size_t cells = (size_t)h[0] * h[1];
+      std::vector<uint8_t> w((ZKB_DFA_HDR + cells * 4 + 15) & ~(size_t)15, 0);
+      memcpy(w.data(), nb.data(), ZKB_DFA_HDR);
+      ((uint32_t*)w.data())[5] = 4;
+      for (size_t i = 0; i < cells; i++) ((uint32_t*)(w.data() + ZKB_DFA_HDR))[i] = ((const uint16_t*)(nb.data() + ZKB_DFA_HDR))[i];
+      nb.swap(w);
+      fe = re = 4;
+    }
+    zkb_regex_set::Part part;
+    part.body = p >= n_header;
+    part.elem = fe;
+    part.fwd_bytes = (uint32_t)fb.size(); part.rev_bytes = (uint32_t)rb.size();
+    if (cudaMalloc((void**)&part.d_fwd, fb.size()) != cudaSuccess || cudaMalloc((void**)&part.d_rev, rb.size()) != cudaSuccess) {
+      zkb_regex_set_destroy(rs);
+      return ZKB_E_NOMEM;
+    }
+    rs->parts.push_back(part);
+    CK(cudaMemcpy(part.d_fwd, fb.data(), fb.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(part.d_rev, rb.data(), rb.size(), cudaMemcpyHostToDevice));
+  }
+  *out = rs;
+  return ZKB_OK;
+}
+
+void zkb_regex_set_destroy(zkb_regex_set* s) {
+  if (!s) return;
+  for (auto& p : s->parts) { if (p.d_fwd) cudaFree(p.d_fwd); if (p.d_rev) cudaFree(p.d_rev); }
+  delete s;
+}
+
+// Pipelined end-to-end batch: pack chunk k+1 on the host while chunk k is on the device.
+int zkb_verify_batch(zkb_engine* e, const zkb_email_view* emails, size_t n, const zkb_regex_set* regex,
+                     const zkb_email_captures* captures, zkb_result* out) {
+  if (!e || (!emails && n) || (!out && n)) return ZKB_E_INVALID;
+  if (regex && regex->eng != e) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lock(e->run_mu);
+  CK(cudaSetDevice(e->device));
+  const size_t CE = e->chunk_emails;
+  const size_t nchunks = (n + CE - 1) / CE;
+  Chunk chunks[3];
+  bool busy[3] = {false, false, false};
+  const size_t P = regex ? regex->n_active() : 0;
+  auto finish = [&](int si) -> int {
+    Slot& s = e->slots[si];
+    Chunk& ch = chunks[si];
+    CK(cudaEventSynchronize(s.done));
+    auto hay = [&](const ThreadRecs& t, const MsgRec& m) { HayView v; v.p = t.blocks[m.blk].p + m.local; v.n = m.len; return v; };
+    resolve_chunk(e, ch, s.result.p, regex, captures, hay, out);
+    release_blocks(e, ch);
+    busy[si] = false;
+    return ZKB_OK;
+  };
+  int rc = ZKB_OK;
+  for (size_t k = 0; k < nchunks && rc == ZKB_OK; k++) {
+    int si = (int)(k % 3);
+    if (busy[si]) rc = finish(si);
+    if (rc) break;
+    Slot& s = e->slots[si];
+    Chunk& ch = chunks[si];
+    size_t e0 = k * CE, ne = std::min(CE, n - e0);
+    rc = pack_chunk(e, emails, e0, ne, regex, ch);
+    if (rc) break;
+    rc = sync_keytab(e, s.stream);
+    if (rc) break;
+    rc = upload_chunk(e, ch, regex, s.dev, s.meta, s.stream);
+    if (rc) break;
+    rc = launch_chunk(e, s.dev, regex, s.stream, nullptr, nullptr);
+    if (rc) break;
+    if (!s.result.ensure(s.dev.out_bytes)) { rc = ZKB_E_NOMEM; break; }
+    CK(cudaMemcpyAsync(s.result.p, s.dev.out.p, s.dev.out_bytes, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaEventRecord(s.done, s.stream));
+    busy[si] = true;
+    // resolve the previous chunk while this one is in flight
+    if (k >= 1) {
+      int pj = (int)((k - 1) % 3);
+      if (busy[pj]) rc = finish(pj);
+    }
+  }
+  for (int si = 0; si < 3; si++) {
+    if (busy[si]) { int r2 = finish(si); if (rc == ZKB_OK) rc = r2; }
+    release_blocks(e, chunks[si]);
+  }
+  (void)P;
+  return rc;
+}
+
+int zkb_verify_one(zkb_engine* e, const zkb_email_view* email, const zkb_regex_set* regex, const zkb_email_captures* captures,
+                   zkb_result* out) {
+  return zkb_verify_batch(e, email, 1, regex, captures, out);
+}
+
+// ---- resident form: prepare (pack + H2D) / run (kernels) / fetch (D2H + resolve) ----
+void zkb_batch_destroy(zkb_batch* b) {
+  if (!b) return;
+  if (b->eng) cudaSetDevice(b->eng->device);
+  for (auto* c : b->chunks) { if (c) { release_blocks(b->eng, *c); delete c; } }
+  for (auto* d : b->dev) { if (d) { d->free(); delete d; } }
+  delete b;
+}
+
+int zkb_batch_prepare(zkb_engine* e, const zkb_email_view* emails, size_t n, const zkb_regex_set* regex,
+                      const zkb_email_captures* captures, zkb_batch** out) {
+  if (!e || !out || (!emails && n)) return ZKB_E_INVALID;
+  if (regex && regex->eng != e) return ZKB_E_INVALID;
+  *out = nullptr;
+  std::lock_guard<std::mutex> lock(e->run_mu);
+  CK(cudaSetDevice(e->device));
+  zkb_batch* b = new zkb_batch();
+  b->eng = e; b->regex = regex; b->n = n; b->emails = emails; b->captures = captures;
+  const size_t CE = e->chunk_emails;
+  cudaStream_t s = e->slots[0].stream;
+  int rc = ZKB_OK;
+  for (size_t e0 = 0; e0 < n && rc == ZKB_OK; e0 += CE) {
+    Chunk* ch = new Chunk();
+    DeviceChunk* d = new DeviceChunk();
+    b->chunks.push_back(ch); b->dev.push_back(d);
+    rc = pack_chunk(e, emails, e0, std::min(CE, n - e0), regex, *ch);
+    if (rc) break;
+    rc = sync_keytab(e, s);
+    if (rc) break;
+    rc = upload_chunk(e, *ch, regex, *d, e->slots[0].meta, s);
+    if (rc) break;
+    if (cudaStreamSynchronize(s) != cudaSuccess) { rc = ZKB_E_CUDA; break; }
+    std::vector<uint8_t>().swap(ch->meta_host);
+  }
+  if (rc) { zkb_batch_destroy(b); return rc; }
+  *out = b;
+  return ZKB_OK;
+}
+
+int zkb_batch_run_async(zkb_batch* b) {
+  if (!b) return ZKB_E_INVALID;
+  zkb_engine* e = b->eng;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = e->slots[0].stream;
+  for (auto* d : b->dev) {
+    // flags and DFA outputs accumulate with atomicOr / plain stores: reset them for a re-run
+    size_t o_flags, o_dfa;
+    out_layout(d->M, d->C, d->NE, d->P, o_flags, o_dfa);
+    CK(cudaMemsetAsync(d->out.p + o_flags, 0, align_up((size_t)d->C * 4, 16), s));
+    int rc = launch_chunk(e, *d, b->regex, s, nullptr, nullptr);
+    if (rc) return rc;
+  }
+  b->ran = true;
+  return ZKB_OK;
+}
+
+int zkb_batch_run(zkb_batch* b) {
+  if (!b) return ZKB_E_INVALID;
+  zkb_engine* e = b->eng;
+  std::lock_guard<std::mutex> lock(e->run_mu);
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = e->slots[0].stream;
+  float acc[5] = {0, 0, 0, 0, 0};
+  CK(cudaEventRecord(e->ev[5], s));
+  for (auto* d : b->dev) {
+    size_t o_flags, o_dfa;
+    out_layout(d->M, d->C, d->NE, d->P, o_flags, o_dfa);
+    CK(cudaMemsetAsync(d->out.p + o_flags, 0, align_up((size_t)d->C * 4, 16), s));
+    int rc = launch_chunk(e, *d, b->regex, s, e->ev, nullptr);
+    if (rc) return rc;
+    CK(cudaEventSynchronize(e->ev[4]));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1])); acc[0] += ms;   // sha256
+    CK(cudaEventElapsedTime(&ms, e->ev[2], e->ev[3])); acc[1] += ms;   // rsa
+    CK(cudaEventElapsedTime(&ms, e->ev[3], e->ev[4])); acc[2] += ms;   // dfa
+    CK(cudaEventElapsedTime(&ms, e->ev[1], e->ev[2])); acc[3] += ms;   // bh check
+  }
+  CK(cudaEventRecord(e->ev[6], s));
+  CK(cudaEventSynchronize(e->ev[6]));
+  CK(cudaEventElapsedTime(&acc[4], e->ev[5], e->ev[6]));
+  memcpy(b->last_ms, acc, sizeof acc);
+  b->ran = true;
+  return ZKB_OK;
+}
+
+int zkb_batch_last_timing(const zkb_batch* b, float ms[5]) {
+  if (!b || !ms) return ZKB_E_INVALID;
+  memcpy(ms, b->last_ms, sizeof b->last_ms);
+  return ZKB_OK;
+}
+
+int zkb_batch_get_stats(const zkb_batch* b, zkb_batch_stats* out) {
+  if (!b || !out) return ZKB_E_INVALID;
+  memset(out, 0, sizeof *out);
+  for (size_t i = 0; i < b->chunks.size(); i++) {
+    const zkb_batch_stats& s = b->chunks[i]->st;
+    out->n_emails += s.n_emails; out->n_candidates += s.n_candidates; out->n_sha_messages += s.n_sha_messages;
+    out->sha_blocks += s.sha_blocks; out->sha_bytes += s.sha_bytes;
+    out->rsa_items_1024 += s.rsa_items_1024; out->rsa_items_2048 += s.rsa_items_2048; out->rsa_items_other += s.rsa_items_other;
+    out->rsa_macs += s.rsa_macs; out->dfa_items += s.dfa_items; out->dfa_bytes += s.dfa_bytes;
+    out->arena_bytes += s.arena_bytes; out->h2d_bytes += s.h2d_bytes;
+    out->d2h_bytes += b->dev[i]->out_bytes;
+    const DeviceChunk& d = *b->dev[i];
+    uint64_t nl = (d.M ? 1 : 0) + (d.C ? 1 : 0);
+    for (int k = 0; k < 6; k++) nl += d.rsa_n[k] ? 1 : 0;
+    if (b->regex && d.n_dfa) nl += b->regex->n_active();
+    out->kernel_launches += nl;
+  }
+  return ZKB_OK;
+}
+
+int zkb_batch_fetch(zkb_batch* b, zkb_result* out) {
+  if (!b || (!out && b->n)) return ZKB_E_INVALID;
+  zkb_engine* e = b->eng;
+  std::lock_guard<std::mutex> lock(e->run_mu);
+  CK(cudaSetDevice(e->device));
+  if (!b->ran) return ZKB_E_INVALID;
+  cudaStream_t s = e->slots[0].stream;
+  PinBuf& res = e->slots[0].result;
+  for (size_t i = 0; i < b->chunks.size(); i++) {
+    Chunk& ch = *b->chunks[i];
+    DeviceChunk& d = *b->dev[i];
+    if (!res.ensure(d.out_bytes)) return ZKB_E_NOMEM;
+    CK(cudaMemcpyAsync(res.p, d.out.p, d.out_bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    auto hay = [&](const ThreadRecs& t, const MsgRec& m) { HayView v; v.p = t.blocks[m.blk].p + m.local; v.n = m.len; return v; };
+    resolve_chunk(e, ch, res.p, b->regex, b->captures, hay, out);
+  }
+  return ZKB_OK;
+}
+
+// ---- regex compiler ----
+int zkb_regex_compile(const char* pattern, size_t pattern_len, uint8_t** fwd, size_t* fwd_len, uint8_t** bwd, size_t* bwd_len,
+                      char* err, size_t err_cap) {
+  if (!pattern || !fwd || !fwd_len || !bwd || !bwd_len) return ZKB_E_INVALID;
+  std::vector<uint8_t> f, r;
+  std::string msg;
+  if (!rx::compile(pattern, pattern_len, f, r, msg)) {
+    if (err && err_cap) { strncpy(err, msg.c_str(), err_cap - 1); err[err_cap - 1] = 0; }
+    return ZKB_E_REGEX;
+  }
+  *fwd = (uint8_t*)malloc(f.size()); *bwd = (uint8_t*)malloc(r.size());
+  if (!*fwd || !*bwd) { free(*fwd); free(*bwd); return ZKB_E_NOMEM; }
+  memcpy(*fwd, f.data(), f.size()); *fwd_len = f.size();
+  memcpy(*bwd, r.data(), r.size()); *bwd_len = r.size();
+  return ZKB_OK;
+}
+void zkb_free(void* p) { free(p); }
+
+// ---- host-only canonicalize_signed_email ----
+int zkb_host_canonicalize(const uint8_t* raw, size_t n, int64_t now_unix, uint8_t** hdr, size_t* hdr_len, uint8_t** body,
+                          size_t* body_len, int* detail) {
+  if ((!raw && n) || !hdr || !hdr_len || !body || !body_len) return ZKB_E_INVALID;
+  int dummy;
+  if (!detail) detail = &dummy;
+  *hdr = *body = nullptr; *hdr_len = *body_len = 0;
+  std::vector<HeaderField> hs;
+  size_t body_off = 0;
+  if (!parse_headers(raw, n, hs, body_off)) { *detail = 1; return ZKB_E_INVALID; }
+  DkimSig sig;
+  std::string scratch;
+  *detail = 2;
+  for (const HeaderField& h : hs) {
+    if (!ieq_ascii(raw + h.key_off, h.key_len, "DKIM-Signature", 14)) continue;
+    if (validate_dkim_header(raw + h.val_off, h.val_len, now_unix, sig) != ZKB_DKIM_PASS) continue;
+    bool hr, br;
+    if (!parse_canon_tag(sig, hr, br)) { *detail = 3; return ZKB_E_INVALID; }
+    uint64_t l = 0;
+    bool has_l = false;
+    if (const Tag* tl = sig.get("l")) { has_l = true; if (!parse_usize_tag(sig, tl, l)) { *detail = 4; return ZKB_E_INVALID; } }
+    const Tag* tb = sig.get("b");
+    std::vector<uint8_t> tmp(tb->val_len + 4);
+    if (base64_decode(sig.val(tb), tb->val_len, tmp.data()) < 0) { *detail = 5; return ZKB_E_INVALID; }
+    size_t bl = 0;
+    const uint8_t* b = find_body(raw, n, bl);
+    uint8_t* ob = (uint8_t*)malloc(bl + 4);
+    uint8_t* oh = (uint8_t*)malloc(preimage_bound(body_off, sig.n));
+    if (!ob || !oh) { free(ob); free(oh); return ZKB_E_NOMEM; }
+    size_t cl = br ? canon_body_relaxed(b, bl, ob) : canon_body_simple(b, bl, ob);
+    if (has_l && l < cl) cl = (size_t)l;
+    *body = ob; *body_len = cl;
+    *hdr = oh; *hdr_len = build_header_preimage(raw, hs, sig, hr, oh, scratch);
+    *detail = 0;
+    return ZKB_OK;
+  }
+  return ZKB_E_INVALID;
+}
+
+// ---- kernel-level entry points (host buffers in / out) ----
+int zkb_sha256_batch(zkb_engine* e, const uint8_t* data, size_t data_len, const uint64_t* off, const uint32_t* len, size_t n,
+                     uint8_t* out) {
+  if (!e || (!out && n) || (n && (!off || !len))) return ZKB_E_INVALID;
+  if (n == 0) return ZKB_OK;
+  std::lock_guard<std::mutex> lock(e->run_mu);
+  CK(cudaSetDevice(e->device));
+  // repack: every message 64-byte aligned and readable one block past its last full block
+  std::vector<uint64_t> noff(n);
+  uint64_t total = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (off[i] + len[i] > data_len) return ZKB_E_INVALID;
+    noff[i] = total; total += (((uint64_t)len[i] >> 6) + 1) << 6;
+  }
+  std::vector<uint8_t> host(total + 64, 0);
+  for (size_t i = 0; i < n; i++) if (len[i]) memcpy(host.data() + noff[i], data + off[i], len[i]);
+  uint8_t* d_arena; uint64_t* d_off; uint32_t* d_len; uint32_t* d_dig;
+  CK(cudaMalloc((void**)&d_arena, host.size()));
+  CK(cudaMalloc((void**)&d_off, n * 8)); CK(cudaMalloc((void**)&d_len, n * 4)); CK(cudaMalloc((void**)&d_dig, n * 32));
+  CK(cudaMemcpy(d_arena, host.data(), host.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_off, noff.data(), n * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_len, len, n * 4, cudaMemcpyHostToDevice));
+  cudaStream_t s = e->slots[0].stream;
+  launch_sha256(d_arena, d_off, d_len, nullptr, (uint32_t)n, d_dig, s);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s));
+  std::vector<uint32_t> dig(n * 8);
+  CK(cudaMemcpy(dig.data(), d_dig, n * 32, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n * 8; i++) { out[4 * i] = (uint8_t)(dig[i] >> 24); out[4 * i + 1] = (uint8_t)(dig[i] >> 16); out[4 * i + 2] = (uint8_t)(dig[i] >> 8); out[4 * i + 3] = (uint8_t)dig[i]; }
+  cudaFree(d_arena); cudaFree(d_off); cudaFree(d_len); cudaFree(d_dig);
+  return ZKB_OK;
+}
+
+int zkb_rsa_verify_batch(zkb_engine* e, const uint8_t* const* key_der, const size_t* key_len, const uint8_t* digests,
+                         const uint8_t* const* sig, const size_t* sig_len, size_t n, uint8_t* ok) {
+  if (!e || (n && (!key_der || !key_len || !digests || !sig || !sig_len || !ok))) return ZKB_E_INVALID;
+  if (n == 0) return ZKB_OK;
+  std::lock_guard<std::mutex> lock(e->run_mu);
+  CK(cudaSetDevice(e->device));
+  ThreadCtx c;
+  ThreadRecs tr;
+  c.eng = e; c.tr = &tr;
+  std::vector<uint32_t> sigw, dig(n * 8);
+  std::vector<RsaItem> lists[6];
+  for (size_t i = 0; i < n; i++) {
+    ok[i] = 0;
+    for (int k = 0; k < 8; k++) dig[i * 8 + k] = ((uint32_t)digests[i * 32 + 4 * k] << 24) | ((uint32_t)digests[i * 32 + 4 * k + 1] << 16) | ((uint32_t)digests[i * 32 + 4 * k + 2] << 8) | digests[i * 32 + 4 * k + 3];
+    KeyMeta km;
+    int32_t id = lookup_key(c, key_der[i], key_len[i], km);
+    if (id < 0) { ok[i] = 2; continue; }
+    if (sig_len[i] != km.k) continue;
+    RsaItem it;
+    it.sig_off = (uint32_t)sigw.size(); it.key_id = (uint32_t)id; it.digest_slot = (uint32_t)i; it.cand = (uint32_t)i;
+    sigw.resize(sigw.size() + km.limbs_class, 0u);
+    for (size_t b = 0; b < sig_len[i]; b++) {
+      size_t bi = sig_len[i] - 1 - b;
+      sigw[it.sig_off + (bi >> 2)] |= (uint32_t)sig[i][b] << (8 * (bi & 3));
+    }
+    lists[rsa_list_of(km)].push_back(it);
+  }
+  cudaStream_t s = e->slots[0].stream;
+  int rc = sync_keytab(e, s);
+  if (rc) return rc;
+  DeviceChunk d;
+  uint32_t *d_sig = nullptr, *d_dig = nullptr, *d_flags = nullptr;
+  RsaItem* d_items[6] = {nullptr};
+  CK(cudaMalloc((void**)&d_sig, std::max<size_t>(16, sigw.size() * 4)));
+  CK(cudaMalloc((void**)&d_dig, n * 32)); CK(cudaMalloc((void**)&d_flags, n * 4));
+  CK(cudaMemcpy(d_sig, sigw.data(), sigw.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_dig, dig.data(), n * 32, cudaMemcpyHostToDevice));
+  CK(cudaMemset(d_flags, 0, n * 4));
+  d.sig_arena = d_sig; d.digests = d_dig; d.cand_flags = d_flags;
+  for (int k = 0; k < 6; k++) {
+    d.rsa_n[k] = (uint32_t)lists[k].size();
+    if (lists[k].empty()) continue;
+    CK(cudaMalloc((void**)&d_items[k], lists[k].size() * sizeof(RsaItem)));
+    CK(cudaMemcpy(d_items[k], lists[k].data(), lists[k].size() * sizeof(RsaItem), cudaMemcpyHostToDevice));
+    d.rsa_items[k] = d_items[k];
+  }
+  rc = launch_chunk(e, d, nullptr, s, nullptr, nullptr);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(s));
+  std::vector<uint32_t> flags(n);
+  CK(cudaMemcpy(flags.data(), d_flags, n * 4, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; i++) if (ok[i] != 2) ok[i] = (flags[i] & ZKB_F_RSA_OK) ? 1 : 0;
+  cudaFree(d_sig); cudaFree(d_dig); cudaFree(d_flags);
+  for (int k = 0; k < 6; k++) if (d_items[k]) cudaFree(d_items[k]);
+  return ZKB_OK;
+}
+
+int zkb_dfa_scan_batch(zkb_engine* e, const zkb_dfa_view* part, const uint8_t* data, size_t data_len, const uint64_t* off,
+                       const uint32_t* len, size_t n, int qp, uint32_t* out) {
+  if (!e || !part || (n && (!off || !len || !out))) return ZKB_E_INVALID;
+  if (n == 0) return ZKB_OK;
+  zkb_regex_set* rs = nullptr;
+  int rc = zkb_regex_set_create(e, part, qp ? 0 : 1, qp ? 1 : 0, 1, 1, &rs);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lock(e->run_mu);
+  CK(cudaSetDevice(e->device));
+  std::vector<DfaItem> items(n);
+  for (size_t i = 0; i < n; i++) {
+    if (off[i] + len[i] > data_len) { zkb_regex_set_destroy(rs); return ZKB_E_INVALID; }
+    items[i].hay_off = off[i]; items[i].hay_len = len[i]; items[i].out_slot = (uint32_t)i;
+  }
+  uint8_t* d_arena; DfaItem* d_items; uint4* d_out;
+  CK(cudaMalloc((void**)&d_arena, data_len + 64)); CK(cudaMalloc((void**)&d_items, n * sizeof(DfaItem))); CK(cudaMalloc((void**)&d_out, n * 16));
+  CK(cudaMemcpy(d_arena, data, data_len, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_items, items.data(), n * sizeof(DfaItem), cudaMemcpyHostToDevice));
+  CK(cudaMemset(d_out, 0, n * 16));
+  const zkb_regex_set::Part& p = rs->parts[0];
+  cudaStream_t s = e->slots[0].stream;
+  launch_dfa(p.elem, d_arena, d_items, (uint32_t)n, p.d_fwd, p.fwd_bytes, p.d_rev, p.rev_bytes, e->smem_optin, qp, d_out, s);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s));
+  CK(cudaMemcpy(out, d_out, n * 16, cudaMemcpyDeviceToHost));
+  cudaFree(d_arena); cudaFree(d_items); cudaFree(d_out);
+  zkb_regex_set_destroy(rs);
+  return ZKB_OK;
+}
+
+int zkb_int_pipe_peaks(zkb_engine* e, double out[8]) {
+  if (!e || !out) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lock(e->run_mu);
+  CK(cudaSetDevice(e->device));
+  for (int i = 0; i < 8; i++) out[i] = 0;
+  uint32_t* d;
+  CK(cudaMalloc((void**)&d, 64));
+  cudaStream_t s = e->slots[0].stream;
+  const int iters = 4096;
+  const unsigned grid = (unsigned)e->sm_count * 8, block = 256;
+  // thread-instructions per launch: IMAD.WIDE: 16 wide MACs x 4 per iteration; others 16 x 4 (IADD3 counts 2 adds -> 1 IADD3)
+  const double per_thread[4] = {iters * 4.0 * 16.0, iters * 4.0 * 16.0, iters * 4.0 * 16.0, iters * 4.0 * 16.0};
+  for (int kind = 0; kind < 4; kind++) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+      CK(cudaEventRecord(e->ev[5], s));
+      launch_int_peak(kind, grid, block, d, 12345u + rep, iters, s);
+      CK(cudaEventRecord(e->ev[6], s));
+      CK(cudaEventSynchronize(e->ev[6]));
+      float ms;
+      CK(cudaEventElapsedTime(&ms, e->ev[5], e->ev[6]));
+      if (rep > 0) best = std::min(best, ms);
+    }
+    out[kind] = per_thread[kind] * grid * block / (best * 1e-3) / 1e9;
+  }
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->device);
+  out[4] = khz / 1000.0;
+  out[5] = e->sm_count;
+  cudaFree(d);
+  return ZKB_OK;
+}
+
+}  // extern "C"

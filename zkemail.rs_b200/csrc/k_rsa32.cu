@@ -1,0 +1,23 @@
+#include "kernels.h"
+#include "rsa.cuh"
+namespace zkb {
+template <bool G>
+static void launch_t(int lanes, const uint32_t* sig_arena, const RsaItem* items, uint32_t n, const uint32_t* keytab,
+                     const uint32_t* digests, uint32_t* cand_flags, cudaStream_t s) {
+  const unsigned block = 128;
+#define ZKB_RSA_CASE(TT)                                                                                  \
+  case TT: {                                                                                              \
+    unsigned grid = (unsigned)(((uint64_t)n * TT + block - 1) / block);                                   \
+    rsa_verify_kernel<32, TT, G><<<grid, block, 0, s>>>(sig_arena, items, n, keytab, digests, cand_flags); \
+    break;                                                                                                \
+  }
+  switch (lanes) { ZKB_RSA_CASE(2) ZKB_RSA_CASE(4) default: ZKB_RSA_CASE(8) }
+#undef ZKB_RSA_CASE
+}
+void launch_rsa32(bool generic, int lanes, const uint32_t* sig_arena, const RsaItem* items, uint32_t n,
+                  const uint32_t* keytab, const uint32_t* digests, uint32_t* cand_flags, cudaStream_t s) {
+  if (!n) return;
+  if (generic) launch_t<true>(lanes, sig_arena, items, n, keytab, digests, cand_flags, s);
+  else launch_t<false>(lanes, sig_arena, items, n, keytab, digests, cand_flags, s);
+}
+}  // namespace zkb

@@ -1,0 +1,33 @@
+// kernels.h — host-callable launchers of the sm_100a kernels (one translation unit per kernel
+// family so that the library builds in parallel).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace zkb {
+
+void launch_sha256(const uint8_t* arena, const uint64_t* msg_off, const uint32_t* msg_len, const uint32_t* order,
+                   uint32_t n, uint32_t* digests, cudaStream_t s);
+void launch_bh_check(const uint32_t* digests, const uint32_t* body_slot, const uint32_t* bh_words, uint32_t n_cand,
+                     uint32_t* cand_flags, cudaStream_t s);
+// limbs in {32,64,128}; lanes = threads cooperating on one signature (clamped to a compiled value)
+void launch_rsa(int limbs, bool generic, int lanes, const uint32_t* sig_arena, const RsaItem* items, uint32_t n,
+                const uint32_t* keytab, const uint32_t* digests, uint32_t* cand_flags, cudaStream_t s);
+void launch_rsa32(bool generic, int lanes, const uint32_t* sig_arena, const RsaItem* items, uint32_t n,
+                  const uint32_t* keytab, const uint32_t* digests, uint32_t* cand_flags, cudaStream_t s);
+void launch_rsa64(bool generic, int lanes, const uint32_t* sig_arena, const RsaItem* items, uint32_t n,
+                  const uint32_t* keytab, const uint32_t* digests, uint32_t* cand_flags, cudaStream_t s);
+void launch_rsa128(bool generic, int lanes, const uint32_t* sig_arena, const RsaItem* items, uint32_t n,
+                   const uint32_t* keytab, const uint32_t* digests, uint32_t* cand_flags, cudaStream_t s);
+cudaError_t dfa_set_smem_limit(size_t bytes);
+void launch_dfa(uint32_t elem, const uint8_t* arena, const DfaItem* items, uint32_t n_items, const uint8_t* fwd_blob,
+                uint32_t fwd_bytes, const uint8_t* rev_blob, uint32_t rev_bytes, size_t smem_limit, int qp, uint4* out,
+                cudaStream_t s);
+void launch_dfa_strided(uint32_t elem, const uint8_t* arena, const DfaItem* items, uint32_t n_emails, uint32_t which,
+                        uint32_t P, uint32_t pi, const uint8_t* fwd_blob, uint32_t fwd_bytes, const uint8_t* rev_blob,
+                        uint32_t rev_bytes, size_t smem_limit, int qp, uint4* out, cudaStream_t s);
+void launch_int_peak(int kind, unsigned grid, unsigned block, uint32_t* out, uint32_t seed, int iters, cudaStream_t s);
+
+}  // namespace zkb

@@ -16,7 +16,7 @@ struct RsaKeyInfo {
   std::vector<uint32_t> n;  // little-endian limbs, minimal
   uint64_t e = 0;
   uint32_t bits = 0, k = 0;   // modulus bits, byte length
-  uint32_t limbs_class = 0;   // 32 / 64 / 96 / 128
+  uint32_t limbs_class = 0;   // 32 / 64 / 128
 };
 
 namespace der {
@@ -86,7 +86,7 @@ inline bool parse_rsa_public_key(const uint8_t* d, size_t len, RsaKeyInfo& out) 
     size_t bi = nl - 1 - i;
     out.n[bi / 4] |= (uint32_t)nv[i] << (8 * (bi % 4));
   }
-  out.limbs_class = limbs <= 32 ? 32 : limbs <= 64 ? 64 : limbs <= 96 ? 96 : 128;
+  out.limbs_class = limbs <= 32 ? 32 : limbs <= 64 ? 64 : 128;  // kernel instantiations
   return true;
 }
 

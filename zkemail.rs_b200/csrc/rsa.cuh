@@ -306,18 +306,4 @@ rsa_verify_kernel(const uint32_t* __restrict__ sig_arena, const RsaItem* __restr
   }
 }
 
-// bh= check: body digest of the candidate vs the decoded bh= value (stored as 8 native words).
-__global__ void bh_check_kernel(const uint32_t* __restrict__ digests,
-                                const uint32_t* __restrict__ body_slot,
-                                const uint32_t* __restrict__ bh_words, uint32_t n_cand,
-                                uint32_t* __restrict__ cand_flags) {
-  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_cand) return;
-  const uint32_t* d = digests + (size_t)body_slot[c] * 8;
-  bool ok = true;
-#pragma unroll
-  for (int i = 0; i < 8; i++) ok = ok && (d[i] == bh_words[(size_t)c * 8 + i]);
-  if (ok) atomicOr(cand_flags + c, ZKB_F_BH_OK);
-}
-
 }  // namespace zkb

@@ -120,49 +120,75 @@ def fold_b64(s: str, first: int = 60, width: int = 72) -> str:
 def synth_body(rng: np.random.Generator, canon_len: int, qp_soft_breaks: bool = False,
                token: Optional[bytes] = None) -> bytes:
     """Printable-ASCII body of lines <= 76 chars + CRLF whose relaxed-canonical length is exactly
-    `canon_len` (SURVEY.md §8d C1/C2 recipe).  No trailing WSP, so canonical == raw here."""
+    `canon_len` (SURVEY.md §8d C1/C2 recipe).  No trailing WSP, so canonical == raw for
+    canon_len >= 3 (shorter bodies are a bare run of letters without a line terminator)."""
+    if canon_len < 3:
+        return b"x" * canon_len
     alphabet = np.frombuffer(
         b"abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789 ,.;:-_()", dtype=np.uint8
     )
-    out = bytearray()
-    token_at = None
-    if token is not None:
-        token_at = int(rng.integers(0, max(1, canon_len - len(token) - 160)))
-    while len(out) < canon_len:
-        remaining = canon_len - len(out)
-        if token is not None and token_at is not None and len(out) >= token_at:
-            line = bytes(token)
-            if qp_soft_breaks and len(line) > 6:
-                cut = int(rng.integers(1, len(line) - 1))
-                line = line[:cut] + b"=\r\n" + line[cut:]
-            out += line + b"\r\n"
-            token_at = None
-            continue
-        if remaining <= 3:
-            # cannot fit a line + CRLF of this size cleanly: extend previous line
-            fill = alphabet[rng.integers(0, 62, size=remaining)].tobytes()
-            if out.endswith(b"\r\n"):
-                out = out[:-2] + fill + b"\r\n"
-            else:
-                out += fill
-            break
-        ll = int(min(rng.integers(40, 77), remaining - 2))
-        if remaining - (ll + 2) in (1, 2):  # avoid an un-fillable 1-2 byte remainder
-            ll = remaining - 2
-            if ll > 76:
-                ll -= 3
-        chars = alphabet[rng.integers(0, len(alphabet), size=ll)]
-        line = bytearray(chars.tobytes())
+
+    def text(n: int) -> bytes:
+        line = bytearray(alphabet[rng.integers(0, len(alphabet), size=n)].tobytes())
         if line[0:1] == b" ":
             line[0:1] = b"x"
         if line[-1:] == b" ":
             line[-1:] = b"x"
-        line = bytes(line)
-        line = re.sub(rb"  +", lambda m: b" " + b"y" * (len(m.group(0)) - 1), line)
-        if qp_soft_breaks and rng.random() < 0.3 and ll > 12 and remaining > ll + 8:
-            line = line[: ll - 3] + b"=\r\n" + line[ll - 3 :]
-        out += line + b"\r\n"
-    body = bytes(out)
+        return re.sub(rb"  +", lambda m: b" " + b"y" * (len(m.group(0)) - 1), bytes(line))
+
+    lines: List[bytes] = []
+    total = 0
+    token_at = None
+    if token is not None:
+        tok_line = bytes(token)
+        if qp_soft_breaks and len(tok_line) > 6:
+            cut = int(rng.integers(1, len(tok_line) - 1))
+            tok_line = tok_line[:cut] + b"=\r\n" + tok_line[cut:]
+        tok_line += b"\r\n"
+        assert canon_len >= len(tok_line) + 3, "body too short for the token line"
+        token_at = int(rng.integers(0, max(1, canon_len - len(tok_line) - 80)))
+    while total < canon_len:
+        remaining = canon_len - total
+        if token_at is not None and total >= token_at and remaining >= len(tok_line):
+            lines.append(tok_line)
+            total += len(tok_line)
+            token_at = None
+            continue
+        budget = remaining - (len(tok_line) if token_at is not None else 0)
+        if budget < 3:
+            budget = remaining
+        ll = int(min(rng.integers(40, 77), budget - 2))
+        left = budget - (ll + 2)
+        if left in (1, 2):
+            ll = ll + left if ll + left <= 76 else ll - (3 - left)
+        ll = max(1, ll)
+        line = text(ll)
+        if qp_soft_breaks and rng.random() < 0.3 and ll > 12:
+            line = line[: ll - 3] + b"=\r\n" + line[ll - 3:]
+            # the soft break adds 3 raw bytes that are part of the canonical body as well
+            if total + len(line) + 2 > canon_len - (len(tok_line) if token_at is not None else 0):
+                line = line[: ll - 3] + line[ll:]
+        lines.append(line + b"\r\n")
+        total += len(lines[-1])
+    body = b"".join(lines)
+    if len(body) != canon_len:  # final adjustment: trim or pad the last text line
+        diff = len(body) - canon_len
+        for i in range(len(lines) - 1, -1, -1):
+            ln = lines[i]
+            if token is not None and ln == tok_line:
+                continue
+            core = ln[:-2]
+            if diff > 0 and len(core) - diff >= 1 and b"=\r\n" not in core[-(diff + 3):]:
+                core = core[: len(core) - diff]
+                if core.endswith(b" "):
+                    core = core[:-1] + b"x"
+                lines[i] = core + b"\r\n"
+                break
+            if diff < 0:
+                lines[i] = core + b"z" * (-diff) + b"\r\n"
+                break
+        body = b"".join(lines)
+    assert len(body) == canon_len, (len(body), canon_len)
     assert relaxed_body(body) == body, "synthetic body must be canonical-stable"
     return body
 
@@ -179,6 +205,7 @@ def sign_email(
     sig_position: str = "top",
     algo: str = "rsa-sha256",
     omit_c: bool = False,
+    meta: Optional[dict] = None,
 ) -> bytes:
     """Build a raw RFC 5322 message with one DKIM-Signature (RFC 6376 §3.5/§3.7)."""
     hc, bc = (canon.split("/") + ["simple"])[:2] if "/" in canon else (canon, "simple")
@@ -213,6 +240,8 @@ def sign_email(
     else:
         pre += simple_header_cfdkim(b"DKIM-Signature", sigv)[:-2]
     sig = key.private.sign(pre, padding.PKCS1v15(), hashes.SHA256())
+    if meta is not None:  # what an RFC 6376 verifier must hash (used to build golden fixtures)
+        meta.update(header_preimage=pre, canonical_body=cbody, signature=sig)
     b = fold_b64(base64.b64encode(sig).decode())
     sig_header = b"DKIM-Signature:" + value_nob.encode() + b.encode() + b"\r\n"
     lines = [k + b":" + v + b"\r\n" for k, v in hdr_bytes]
