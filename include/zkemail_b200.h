@@ -196,8 +196,9 @@ int zkb_dfa_scan_batch(zkb_engine *e, const zkb_dfa_view *part, const uint8_t *d
                        size_t data_len, const uint64_t *off, const uint32_t *len, size_t n, int qp,
                        uint32_t *out);
 /* Integer-pipe peak microbenchmarks (register-only): giga thread-instructions per second for
- * [0]=IMAD.WIDE.U32 (dependent chains, 32x32+64) [1]=IADD3 [2]=LOP3 [3]=SHF  plus [4]=SM clock MHz
- * observed by the kernel (clock64 vs events). Used as roofline denominators. */
+ * [0]=IMAD.WIDE.U32(.X) (carry chains, 32x32+64 -> 64, the RSA inner instruction) [1]=IADD3 [2]=LOP3
+ * [3]=SHF, then [4]=SM clock MHz (device attribute) [5]=SM count.  Used as the roofline denominators
+ * of the integer-bound kernels (MEASURED_PEAKS.json has no integer peak). */
 int zkb_int_pipe_peaks(zkb_engine *e, double out[8]);
 
 /*

@@ -9,6 +9,9 @@
 #include <stdint.h>
 #include <string.h>
 #include <time.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <string>
 #include <vector>
@@ -140,59 +143,77 @@ struct DkimSig {
 };
 
 namespace detail {
-inline bool fws(uint8_t c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n'; }
-inline bool valchar(uint8_t c) { return (c >= 0x21 && c <= 0x3A) || (c >= 0x3C && c <= 0x7E); }
-inline bool alpha(uint8_t c) { return (uint8_t)((c | 32) - 'a') < 26; }
-inline bool alnum_(uint8_t c) { return alpha(c) || (uint8_t)(c - '0') < 10 || c == '_'; }
+enum { C_FWS = 1, C_VAL = 2, C_ALPHA = 4, C_ALNUM = 8 };
+struct CharTab {
+  uint8_t t[256];
+  CharTab() {
+    for (int c = 0; c < 256; c++) {
+      uint8_t v = 0;
+      if (c == ' ' || c == '\t' || c == '\r' || c == '\n') v |= C_FWS;
+      if ((c >= 0x21 && c <= 0x3A) || (c >= 0x3C && c <= 0x7E)) v |= C_VAL;
+      bool al = (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z');
+      if (al) v |= C_ALPHA;
+      if (al || (c >= '0' && c <= '9') || c == '_') v |= C_ALNUM;
+      t[c] = v;
+    }
+  }
+};
+inline const uint8_t* chartab() { static const CharTab T; return T.t; }
 }  // namespace detail
 
 // cfdkim parser::tag_list + lib.rs::validate_header.  Returns ZKB_DKIM_PASS or the error kind.
 inline int validate_dkim_header(const uint8_t* raw_val, size_t raw_len, int64_t now_unix, DkimSig& sig) {
   using namespace detail;
+  const uint8_t* CT = chartab();
   sig.tags.clear();
   sig.vals.clear();
   bool ascii = true;
-  for (size_t i = 0; i < raw_len; i++) if (raw_val[i] & 0x80) { ascii = false; break; }
+  {
+    size_t i = 0;
+    uint64_t acc = 0;
+    for (; i + 8 <= raw_len; i += 8) { uint64_t w; memcpy(&w, raw_val + i, 8); acc |= w; }
+    for (; i < raw_len; i++) acc |= raw_val[i];
+    ascii = (acc & 0x8080808080808080ull) == 0;
+  }
   if (ascii) { sig.s = raw_val; sig.n = raw_len; }
   else { utf8_lossy(raw_val, raw_len, sig.lossy); sig.s = (const uint8_t*)sig.lossy.data(); sig.n = sig.lossy.size(); }
   const uint8_t* s = sig.s;
   const size_t n = sig.n;
+  sig.vals.reserve(n);
   size_t pos = 0;
   bool first = true;
   for (;;) {
-    size_t save_vals = sig.vals.size();
     size_t p = pos;
     if (!first) {
       if (p >= n || s[p] != ';') break;
       p++;
     }
-    while (p < n && fws(s[p])) p++;
-    if (p >= n || !alpha(s[p])) { if (first) return ZKB_DKIM_SYNTAX; break; }
+    while (p < n && (CT[s[p]] & C_FWS)) p++;
+    if (p >= n || !(CT[s[p]] & C_ALPHA)) { if (first) return ZKB_DKIM_SYNTAX; break; }
     Tag t;
     t.name_off = (uint32_t)p;
-    while (p < n && alnum_(s[p])) p++;
+    while (p < n && (CT[s[p]] & C_ALNUM)) p++;
     t.name_len = (uint32_t)(p - t.name_off);
-    while (p < n && fws(s[p])) p++;
+    while (p < n && (CT[s[p]] & C_FWS)) p++;
     if (p >= n || s[p] != '=') { if (first) return ZKB_DKIM_SYNTAX; break; }
     p++;
-    while (p < n && fws(s[p])) p++;
+    while (p < n && (CT[s[p]] & C_FWS)) p++;
     t.raw_off = (uint32_t)p; t.raw_len = 0;
     t.val_off = (uint32_t)sig.vals.size();
-    if (p < n && valchar(s[p])) {
+    if (p < n && (CT[s[p]] & C_VAL)) {
       for (;;) {
         size_t a = p;
-        while (p < n && valchar(s[p])) p++;
+        while (p < n && (CT[s[p]] & C_VAL)) p++;
         sig.vals.append((const char*)s + a, p - a);
         t.raw_len = (uint32_t)(p - t.raw_off);
         size_t q = p;
-        while (q < n && fws(s[q])) q++;
-        if (q == p || q >= n || !valchar(s[q])) break;
+        while (q < n && (CT[s[q]] & C_FWS)) q++;
+        if (q == p || q >= n || !(CT[s[q]] & C_VAL)) break;
         p = q;
       }
     }
     t.val_len = (uint32_t)(sig.vals.size() - t.val_off);
-    while (p < n && fws(s[p])) p++;
-    (void)save_vals;
+    while (p < n && (CT[s[p]] & C_FWS)) p++;
     // IndexMap insert: a later duplicate replaces the value in the first one's position
     bool dup = false;
     for (Tag& o : sig.tags)
@@ -267,23 +288,41 @@ inline bool parse_usize_tag(const DkimSig& sig, const Tag* t, uint64_t& out) {
 }
 
 // ------------------------------------------------------------------ canonicalisation (single pass)
-// Relaxed body; out must hold n + 2 bytes.
+// Relaxed body; out must hold n + 2 bytes.  Single pass with the state (o, prev_sp); 16-byte chunks
+// that the state machine would copy verbatim (no TAB, no SP followed by SP/CR, not ending in SP, not
+// starting with LF, and not directly after a SP) take an SSE2 fast path.
 inline size_t canon_body_relaxed(const uint8_t* in, size_t n, uint8_t* out) {
-  size_t o = 0;
+  size_t o = 0, i = 0;
   bool prev_sp = false;
-  for (size_t i = 0; i < n; i++) {
-    uint8_t c = in[i];
-    if (c == ' ' || c == '\t') {
-      if (!prev_sp) { out[o++] = ' '; prev_sp = true; }
-      continue;
+  auto scalar = [&](size_t end) {
+    for (; i < end; i++) {
+      uint8_t c = in[i];
+      if (c == ' ' || c == '\t') {
+        if (!prev_sp) { out[o++] = ' '; prev_sp = true; }
+        continue;
+      }
+      prev_sp = false;
+      if (c == '\n' && o >= 2 && out[o - 1] == '\r' && out[o - 2] == ' ') {
+        out[o - 2] = '\r'; out[o - 1] = '\n';  // drop the single SP before CRLF
+        continue;
+      }
+      out[o++] = c;
     }
-    prev_sp = false;
-    if (c == '\n' && o >= 2 && out[o - 1] == '\r' && out[o - 2] == ' ') {
-      out[o - 2] = '\r'; out[o - 1] = '\n';  // drop the single SP before CRLF
-      continue;
-    }
-    out[o++] = c;
+  };
+#if defined(__SSE2__)
+  const __m128i vsp = _mm_set1_epi8(' '), vtab = _mm_set1_epi8('\t'), vcr = _mm_set1_epi8('\r');
+  while (i + 16 <= n) {
+    __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(in + i));
+    unsigned sp = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(v, vsp));
+    unsigned tab = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(v, vtab));
+    unsigned cr = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(v, vcr));
+    unsigned bad = tab | (sp & ((sp | cr) >> 1)) | (sp & 0x8000u);
+    if (bad | (unsigned)prev_sp | (unsigned)(in[i] == '\n')) { scalar(i + 16); continue; }
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(out + o), v);
+    o += 16; i += 16;
   }
+#endif
+  scalar(n);
   while (o >= 4 && out[o - 1] == '\n' && out[o - 2] == '\r' && out[o - 3] == '\n' && out[o - 4] == '\r') o -= 2;
   if (o > 0 && !(o >= 2 && out[o - 2] == '\r' && out[o - 1] == '\n')) { out[o++] = '\r'; out[o++] = '\n'; }
   return o;
@@ -384,15 +423,22 @@ inline size_t build_header_preimage(const uint8_t* raw, const std::vector<Header
   const uint8_t* v = sig.s;
   size_t vl = sig.n;
   if (tb->raw_len != 0) {
+    // value.replace(raw_b, ""): every (non-overlapping, left to right) occurrence of the raw b= text
     scratch.clear();
     const uint8_t* pat = sig.s + tb->raw_off;
-    size_t pl = tb->raw_len, i = 0;
-    while (i < vl) {
-      const uint8_t* f = (i + pl <= vl) ? (const uint8_t*)memmem(sig.s + i, vl - i, pat, pl) : nullptr;
-      if (!f) { scratch.append((const char*)sig.s + i, vl - i); break; }
-      scratch.append((const char*)sig.s + i, (size_t)(f - (sig.s + i)));
-      i = (size_t)(f - sig.s) + pl;
+    const size_t pl = tb->raw_len;
+    size_t i = 0, copied = 0;
+    while (i + pl <= vl) {
+      const uint8_t* f = (const uint8_t*)memchr(sig.s + i, pat[0], vl - pl - i + 1);
+      if (!f) break;
+      i = (size_t)(f - sig.s);
+      if (memcmp(f, pat, pl) == 0) {
+        scratch.append((const char*)sig.s + copied, i - copied);
+        i += pl;
+        copied = i;
+      } else i++;
     }
+    scratch.append((const char*)sig.s + copied, vl - copied);
     v = (const uint8_t*)scratch.data(); vl = scratch.size();
   }
   size_t w = relaxed ? canon_header_relaxed((const uint8_t*)"DKIM-Signature", 14, v, vl, out + o)
@@ -400,8 +446,14 @@ inline size_t build_header_preimage(const uint8_t* raw, const std::vector<Header
   return o + w - 2;
 }
 
-// bytes::get_all_after(raw, "\r\n\r\n")
-inline const uint8_t* find_body(const uint8_t* raw, size_t n, size_t& blen) {
+// bytes::get_all_after(raw, "\r\n\r\n").  hdr_end (optional) = end of the header block found by
+// parse_headers: when the block ends in CRLF CRLF that is necessarily the FIRST CRLF CRLF of the
+// message (an earlier one would have ended the block earlier), so no search is needed.
+inline const uint8_t* find_body(const uint8_t* raw, size_t n, size_t& blen, size_t hdr_end = 0) {
+  if (hdr_end >= 4 && hdr_end <= n && memcmp(raw + hdr_end - 4, "\r\n\r\n", 4) == 0) {
+    blen = n - hdr_end;
+    return raw + hdr_end;
+  }
   const uint8_t* f = n >= 4 ? (const uint8_t*)memmem(raw, n, "\r\n\r\n", 4) : nullptr;
   if (!f) { blen = 0; return raw + n; }
   blen = n - (size_t)(f - raw) - 4;

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -226,7 +227,6 @@ struct Chunk {  // host view of one chunk
   size_t e0 = 0, ne = 0;
   std::vector<EmailRec> emails;
   std::vector<ThreadRecs> tr;
-  std::vector<uint8_t> meta_host;  // staged in pageable memory, copied through the slot's pinned meta
   zkb_batch_stats st;
   size_t arena_bytes = 0, meta_bytes = 0;
   uint32_t M = 0, C = 0;
@@ -296,6 +296,8 @@ struct ThreadCtx {
   std::string scratch;
   std::vector<uint8_t> tmp;
   std::unordered_map<std::string, std::pair<int32_t, KeyMeta>> key_cache;
+  struct PtrKey { const uint8_t* p = nullptr; size_t len = 0; int32_t id = 0; KeyMeta meta; };
+  PtrKey ptr_cache[64];  // same buffer => same bytes: skips the content hash for pooled keys
   std::unordered_map<std::string, uint32_t> dom_msgs;
   std::unordered_map<int32_t, uint32_t> key_msgs;
   std::string last_dom; uint32_t last_dom_msg = 0; bool have_last_dom = false;
@@ -332,9 +334,15 @@ struct ThreadCtx {
 };
 
 int32_t lookup_key(ThreadCtx& c, const uint8_t* der, size_t len, KeyMeta& meta) {
+  ThreadCtx::PtrKey& pk = c.ptr_cache[((uintptr_t)der >> 4) & 63];
+  if (pk.p == der && pk.len == len) { meta = pk.meta; return pk.id; }
   std::string k((const char*)der, len);
   auto it = c.key_cache.find(k);
-  if (it != c.key_cache.end()) { meta = it->second.second; return it->second.first; }
+  if (it != c.key_cache.end()) {
+    meta = it->second.second;
+    pk.p = der; pk.len = len; pk.id = it->second.first; pk.meta = meta;
+    return it->second.first;
+  }
   zkb_engine* e = c.eng;
   int32_t id;
   meta = KeyMeta();
@@ -358,6 +366,7 @@ int32_t lookup_key(ThreadCtx& c, const uint8_t* der, size_t len, KeyMeta& meta) 
     if (id >= 0) meta = e->key_meta[id];
   }
   c.key_cache.emplace(std::move(k), std::make_pair(id, meta));
+  pk.p = der; pk.len = len; pk.id = id; pk.meta = meta;
   return id;
 }
 
@@ -390,7 +399,7 @@ void process_email(ThreadCtx& c, const zkb_email_view& em, bool want_regex, int 
   auto body_msg_for = [&](bool relaxed, bool has_l, uint64_t l) -> uint32_t {
     for (int i = 0; i < n_bodies; i++)
       if (bodies[i].relaxed == relaxed && bodies[i].has_l == has_l && bodies[i].l == l) return bodies[i].msg;
-    if (!body_found) { body = find_body(raw, n, body_len); body_found = true; }
+    if (!body_found) { body = find_body(raw, n, body_len, body_off); body_found = true; }
     uint32_t blk, local;
     uint8_t* p = c.reserve((((body_len + 2) >> 6) + 1) << 6, blk, local);
     if (!p) return 0;
@@ -508,10 +517,12 @@ void process_email(ThreadCtx& c, const zkb_email_view& em, bool want_regex, int 
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+double g_prof_parse = 0, g_prof_layout = 0;  // ZKB_PROFILE accounting (single caller per engine)
+inline double now_s2() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 inline int rsa_list_of(const KeyMeta& k) { return (k.limbs_class == 32 ? 0 : k.limbs_class == 64 ? 1 : 2) * 2 + (k.generic ? 1 : 0); }
 
 // Host pack of emails [e0, e0+ne): parallel parse + layout of the SoA meta buffers.
-int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne, const zkb_regex_set* rs, Chunk& ch) {
+int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne, const zkb_regex_set* rs, Chunk& ch, PinBuf& pin_meta) {
   const int T = e->pool->size();
   ch.e0 = e0; ch.ne = ne;
   ch.emails.assign(ne, EmailRec());
@@ -520,6 +531,7 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
   const bool want_regex = rs != nullptr;
   std::atomic<size_t> next{0};
   std::atomic<int> oom{0};
+  const double tp0 = now_s2();
   const size_t grain = std::max<size_t>(16, std::min<size_t>(512, ne / (size_t)(T * 8) + 1));
   e->pool->run([&](int tid) {
     ThreadCtx c;
@@ -535,6 +547,8 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
     }
   });
   if (oom) return ZKB_E_NOMEM;
+  const double tp1 = now_s2();
+  g_prof_parse += tp1 - tp0;
   // layout: device arena = concatenation of the used parts of all staging blocks
   uint64_t off = 0;
   uint32_t M = 0, C = 0;
@@ -567,8 +581,8 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
   for (int k = 0; k < 6; k++) { ch.o_rsa[k] = o; ch.rsa_n[k] = rn[k]; o += align_up((size_t)rn[k] * sizeof(RsaItem), 16); }
   ch.o_dfa = o; o += align_up((size_t)n_dfa * 2 * sizeof(DfaItem), 16);  // header haystack + body haystack per email
   ch.meta_bytes = o + 16;
-  ch.meta_host.assign(ch.meta_bytes, 0);
-  uint8_t* mh = ch.meta_host.data();
+  if (!pin_meta.ensure(ch.meta_bytes)) return ZKB_E_NOMEM;
+  uint8_t* mh = pin_meta.p;  // every array below is written in full; padding bytes are never read
   uint64_t* msg_off = (uint64_t*)(mh + ch.o_msg_off);
   uint32_t* msg_len = (uint32_t*)(mh + ch.o_msg_len);
   uint32_t* order = (uint32_t*)(mh + ch.o_order);
@@ -660,6 +674,7 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
   ch.st.dfa_items = (uint64_t)n_dfa * P; ch.st.dfa_bytes = dfa_bytes;
   ch.st.arena_bytes = ch.arena_bytes;
   ch.st.h2d_bytes = off + ch.meta_bytes;
+  g_prof_layout += now_s2() - tp1;
   return ZKB_OK;
 }
 
@@ -677,8 +692,6 @@ int upload_chunk(zkb_engine* e, Chunk& ch, const zkb_regex_set* rs, DeviceChunk&
   size_t o_flags, o_dfa;
   d.out_bytes = out_layout(ch.M, ch.C, ch.ne, P, o_flags, o_dfa);
   if (!d.out.ensure(d.out_bytes)) return ZKB_E_NOMEM;
-  if (!pin_meta.ensure(ch.meta_bytes)) return ZKB_E_NOMEM;
-  memcpy(pin_meta.p, ch.meta_host.data(), ch.meta_bytes);
   for (auto& t : ch.tr)
     for (auto& b : t.blocks)
       if (b.used) CK(cudaMemcpyAsync(d.arena.p + b.dev_off, b.p, b.used, cudaMemcpyHostToDevice, stream));
@@ -996,6 +1009,10 @@ void zkb_regex_set_destroy(zkb_regex_set* s) {
   delete s;
 }
 
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 // Pipelined end-to-end batch: pack chunk k+1 on the host while chunk k is on the device.
 int zkb_verify_batch(zkb_engine* e, const zkb_email_view* emails, size_t n, const zkb_regex_set* regex,
                      const zkb_email_captures* captures, zkb_result* out) {
@@ -1008,14 +1025,21 @@ int zkb_verify_batch(zkb_engine* e, const zkb_email_view* emails, size_t n, cons
   Chunk chunks[3];
   bool busy[3] = {false, false, false};
   const size_t P = regex ? regex->n_active() : 0;
+  const bool prof = getenv("ZKB_PROFILE") != nullptr;
+  double t_pack = 0, t_upload = 0, t_wait = 0, t_resolve = 0, t_all = now_s();
+  g_prof_parse = g_prof_layout = 0;
   auto finish = [&](int si) -> int {
     Slot& s = e->slots[si];
     Chunk& ch = chunks[si];
+    double ta = now_s();
     CK(cudaEventSynchronize(s.done));
+    double tb = now_s();
+    t_wait += tb - ta;
     auto hay = [&](const ThreadRecs& t, const MsgRec& m) { HayView v; v.p = t.blocks[m.blk].p + m.local; v.n = m.len; return v; };
     resolve_chunk(e, ch, s.result.p, regex, captures, hay, out);
     release_blocks(e, ch);
     busy[si] = false;
+    t_resolve += now_s() - tb;
     return ZKB_OK;
   };
   int rc = ZKB_OK;
@@ -1026,8 +1050,11 @@ int zkb_verify_batch(zkb_engine* e, const zkb_email_view* emails, size_t n, cons
     Slot& s = e->slots[si];
     Chunk& ch = chunks[si];
     size_t e0 = k * CE, ne = std::min(CE, n - e0);
-    rc = pack_chunk(e, emails, e0, ne, regex, ch);
+    double t0 = now_s();
+    rc = pack_chunk(e, emails, e0, ne, regex, ch, s.meta);
     if (rc) break;
+    double t1 = now_s();
+    t_pack += t1 - t0;
     rc = sync_keytab(e, s.stream);
     if (rc) break;
     rc = upload_chunk(e, ch, regex, s.dev, s.meta, s.stream);
@@ -1038,6 +1065,7 @@ int zkb_verify_batch(zkb_engine* e, const zkb_email_view* emails, size_t n, cons
     CK(cudaMemcpyAsync(s.result.p, s.dev.out.p, s.dev.out_bytes, cudaMemcpyDeviceToHost, s.stream));
     CK(cudaEventRecord(s.done, s.stream));
     busy[si] = true;
+    t_upload += now_s() - t1;
     // resolve the previous chunk while this one is in flight
     if (k >= 1) {
       int pj = (int)((k - 1) % 3);
@@ -1049,6 +1077,10 @@ int zkb_verify_batch(zkb_engine* e, const zkb_email_view* emails, size_t n, cons
     release_blocks(e, chunks[si]);
   }
   (void)P;
+  if (prof)
+    fprintf(stderr, "[zkb profile] n=%zu chunks=%zu threads=%d total=%.1fms pack=%.1f (parse %.1f, layout %.1f) upload+launch=%.1f wait_gpu=%.1f resolve=%.1f\n",
+            n, nchunks, e->pool->size(), 1e3 * (now_s() - t_all), 1e3 * t_pack, 1e3 * g_prof_parse, 1e3 * g_prof_layout, 1e3 * t_upload,
+            1e3 * t_wait, 1e3 * t_resolve);
   return rc;
 }
 
@@ -1075,21 +1107,20 @@ int zkb_batch_prepare(zkb_engine* e, const zkb_email_view* emails, size_t n, con
   CK(cudaSetDevice(e->device));
   zkb_batch* b = new zkb_batch();
   b->eng = e; b->regex = regex; b->n = n; b->emails = emails; b->captures = captures;
-  const size_t CE = e->chunk_emails;
+  const size_t CE = e->chunk_emails * 8;  // resident batches: fewer, larger launches
   cudaStream_t s = e->slots[0].stream;
   int rc = ZKB_OK;
   for (size_t e0 = 0; e0 < n && rc == ZKB_OK; e0 += CE) {
     Chunk* ch = new Chunk();
     DeviceChunk* d = new DeviceChunk();
     b->chunks.push_back(ch); b->dev.push_back(d);
-    rc = pack_chunk(e, emails, e0, std::min(CE, n - e0), regex, *ch);
+    rc = pack_chunk(e, emails, e0, std::min(CE, n - e0), regex, *ch, e->slots[0].meta);
     if (rc) break;
     rc = sync_keytab(e, s);
     if (rc) break;
     rc = upload_chunk(e, *ch, regex, *d, e->slots[0].meta, s);
     if (rc) break;
     if (cudaStreamSynchronize(s) != cudaSuccess) { rc = ZKB_E_CUDA; break; }
-    std::vector<uint8_t>().swap(ch->meta_host);
   }
   if (rc) { zkb_batch_destroy(b); return rc; }
   *out = b;
@@ -1231,7 +1262,7 @@ int zkb_host_canonicalize(const uint8_t* raw, size_t n, int64_t now_unix, uint8_
     std::vector<uint8_t> tmp(tb->val_len + 4);
     if (base64_decode(sig.val(tb), tb->val_len, tmp.data()) < 0) { *detail = 5; return ZKB_E_INVALID; }
     size_t bl = 0;
-    const uint8_t* b = find_body(raw, n, bl);
+    const uint8_t* b = find_body(raw, n, bl, body_off);
     uint8_t* ob = (uint8_t*)malloc(bl + 4);
     uint8_t* oh = (uint8_t*)malloc(preimage_bound(body_off, sig.n));
     if (!ob || !oh) { free(ob); free(oh); return ZKB_E_NOMEM; }
@@ -1375,8 +1406,10 @@ int zkb_int_pipe_peaks(zkb_engine* e, double out[8]) {
   cudaStream_t s = e->slots[0].stream;
   const int iters = 4096;
   const unsigned grid = (unsigned)e->sm_count * 8, block = 256;
-  // thread-instructions per launch: IMAD.WIDE: 16 wide MACs x 4 per iteration; others 16 x 4 (IADD3 counts 2 adds -> 1 IADD3)
-  const double per_thread[4] = {iters * 4.0 * 16.0, iters * 4.0 * 16.0, iters * 4.0 * 16.0, iters * 4.0 * 16.0};
+  // thread-instructions per launch.  kind 0: each asm block is 16 PTX mad.lo/madc.hi instructions that
+  // ptxas fuses pairwise into 8 IMAD.WIDE.U32(.X) (checked in SASS), 4 blocks per iteration; kinds 1-3:
+  // 16 independent IADD3 / LOP3 / SHF per block (the two PTX adds fuse into one 3-input IADD3).
+  const double per_thread[4] = {iters * 4.0 * 8.0, iters * 4.0 * 16.0, iters * 4.0 * 16.0, iters * 4.0 * 16.0};
   for (int kind = 0; kind < 4; kind++) {
     float best = 1e30f;
     for (int rep = 0; rep < 4; rep++) {
