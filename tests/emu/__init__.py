@@ -79,19 +79,19 @@ def regex_compile(pattern: bytes):
     return r
 
 
-def dfa_scan(fwd, bwd, hays, qp=False, use_smem=True):
+def dfa_scan(fwd, bwd, hays, qp=False, use_smem=True, table_form=0):
     n = len(hays)
     off, cur = [], 0
     for h in hays:
         off.append(cur)
         cur += (len(h) // 64 + 1) * 64
-    arena = np.full(cur + 64, 0x41, dtype=np.uint8)
+    arena = np.full(cur + 64, 0x3D, dtype=np.uint8)  # '=' garbage in the padding: must never be read as data
     for o, h in zip(off, hays):
         arena[o:o + len(h)] = np.frombuffer(h, dtype=np.uint8)
     offa = np.array(off, dtype=np.uint64)
     lena = np.array([len(h) for h in hays], dtype=np.uint32)
     out = np.zeros((n, 4), dtype=np.uint32)
     rc = lib().emu_dfa_scan(fwd, len(fwd), bwd, len(bwd), _p(arena), _p(offa), _p(lena), n, 1 if qp else 0,
-                            1 if use_smem else 0, _p(out))
+                            1 if use_smem else 0, _p(out), table_form)
     assert rc == 0
     return out

@@ -80,33 +80,32 @@ int emu_regex_compile(const char* pat, size_t len, uint8_t** fwd, size_t* fl, ui
 }
 void emu_free(void* p) { free(p); }
 
-// out = n x uint4 (count, start, end, panic)
+// out = n x uint4 (count, start, end, panic).  table_form: 0 = as the engine chooses, 1 = force
+// class-compressed u16/u32, 2 = force u32 elements
 int emu_dfa_scan(const uint8_t* fwd, size_t fl, const uint8_t* bwd, size_t bl, const uint8_t* arena,
-                 const uint64_t* off, const uint32_t* len, uint32_t n, int qp, int use_smem, uint32_t* out) {
+                 const uint64_t* off, const uint32_t* len, uint32_t n, int qp, int use_smem, uint32_t* out, int table_form) {
   std::vector<uint8_t> fb, rb;
-  uint32_t fe, re;
-  if (!build_dfa_blob(fwd, fl, false, fb, fe) || !build_dfa_blob(bwd, bl, true, rb, re)) return 1;
+  uint32_t elem = 2;
+  bool direct = false;
+  if (table_form == 0) {
+    if (!build_dfa_pair(fwd, fl, bwd, bl, fb, rb, elem, direct)) return 1;
+  } else {
+    uint32_t e1, e2;
+    elem = table_form == 2 ? 4 : 0;
+    if (!build_dfa_blob(fwd, fl, false, false, elem, fb, e1) || !build_dfa_blob(bwd, bl, true, false, elem ? elem : e1, rb, e2)) return 1;
+    if (e1 != e2) {  // re-encode both as u32
+      if (!build_dfa_blob(fwd, fl, false, false, 4, fb, e1) || !build_dfa_blob(bwd, bl, true, false, 4, rb, e2)) return 1;
+    }
+    elem = e1;
+  }
   std::vector<DfaItem> items(n);
   for (uint32_t i = 0; i < n; i++) { items[i].hay_off = off[i]; items[i].hay_len = len[i]; items[i].out_slot = i; }
   const unsigned block = 128;
-  bool wide = fe == 4 || re == 4;
-  if (wide) {  // the kernel uses one element width for both tables
-    std::vector<uint8_t> t;
-    // re-encode a 16-bit table as 32-bit
-    auto widen = [&](std::vector<uint8_t>& b, uint32_t e) {
-      if (e == 4) return;
-      size_t cells = (size_t)((uint32_t*)b.data())[0] * ((uint32_t*)b.data())[1];
-      t.assign((ZKB_DFA_HDR + cells * 4 + 15) & ~(size_t)15, 0);
-      memcpy(t.data(), b.data(), ZKB_DFA_HDR);
-      ((uint32_t*)t.data())[5] = 4;
-      for (size_t i = 0; i < cells; i++) ((uint32_t*)(t.data() + ZKB_DFA_HDR))[i] = ((uint16_t*)(b.data() + ZKB_DFA_HDR))[i];
-      b.swap(t);
-    };
-    widen(fb, fe); widen(rb, re);
-  }
   emu::launch((n + block - 1) / block, block, [&]() {
-    if (wide) dfa_scan_kernel<uint32_t>(arena, items.data(), n, fb.data(), (uint32_t)fb.size(), rb.data(), (uint32_t)rb.size(), use_smem, qp, (uint4*)out);
-    else dfa_scan_kernel<uint16_t>(arena, items.data(), n, fb.data(), (uint32_t)fb.size(), rb.data(), (uint32_t)rb.size(), use_smem, qp, (uint4*)out);
+#define RUN(TT, D) dfa_scan_kernel<TT, D>(arena, items.data(), n, fb.data(), (uint32_t)fb.size(), rb.data(), (uint32_t)rb.size(), use_smem, qp, (uint4*)out)
+    if (elem == 2) { if (direct) RUN(uint16_t, true); else RUN(uint16_t, false); }
+    else { if (direct) RUN(uint32_t, true); else RUN(uint32_t, false); }
+#undef RUN
   });
   return 0;
 }

@@ -151,6 +151,10 @@ def _hays(seed):
     for _ in range(70):
         l = int(rng.integers(0, 40))
         hays.append(bytes(alpha[i] for i in rng.integers(0, len(alpha), size=l)))
+    words = [b"from:", b"subject:", b"abc", b"aaa", b" ", b"\r\n", b"Transaction ID: ", b"X9", b"hello", b"=\r\n", b"=", b"@example.com", b"3.14", b"to:"]
+    for _ in range(40):   # long haystacks: the unrolled 16-byte block path
+        k = int(rng.integers(5, 60))
+        hays.append(b"".join(words[i] for i in rng.integers(0, len(words), size=k)))
     return hays
 
 
@@ -164,18 +168,20 @@ def test_regex_compiler_oracle_search_and_dfa_kernel_source(pat, pypat):
     for h, e in zip(hays, exp):
         cnt, spans = oracle.dfa_find_iter(fwd, bwd, h, 64)
         assert cnt == len(e) and spans == e[:64], (pat, h, e, spans)
-    got = emu.dfa_scan(fwd, bwd, hays, qp=False, use_smem=True)
-    for h, e, r in zip(hays, exp, got):
-        c, s, en, panic = (int(x) for x in r)
-        assert c == len(e) and not panic and (not e or (s, en) == e[0]), (pat, h, e, r)
+    for form in (0, 1, 2):   # DIRECT rows (engine's choice for small DFAs), class-compressed, u32 elements
+        got = emu.dfa_scan(fwd, bwd, hays, qp=False, use_smem=(form != 2), table_form=form)
+        for h, e, r in zip(hays, exp, got):
+            c, s, en, panic = (int(x) for x in r)
+            assert c == len(e) and not panic and (not e or (s, en) == e[0]), (pat, form, h, e, r)
     # fused quoted-printable soft-break removal vs the oracle on the cleaned copy
     hq = [h.replace(b"b", b"b=\r\n", 1) if i % 2 else h + b"=\r\n" for i, h in enumerate(hays)]
-    got = emu.dfa_scan(fwd, bwd, hq, qp=True, use_smem=False)
-    for h, r in zip(hq, got):
-        clean, _ = oracle.qp_clean(h)
-        cnt, spans = oracle.dfa_find_iter(fwd, bwd, clean, 4)
-        c, s, en, panic = (int(x) for x in r)
-        assert c == cnt and not panic and (not cnt or (s, en) == spans[0]), (pat, h, clean, spans, r)
+    for form in (0, 1):
+        got = emu.dfa_scan(fwd, bwd, hq, qp=True, use_smem=False, table_form=form)
+        for h, r in zip(hq, got):
+            clean, _ = oracle.qp_clean(h)
+            cnt, spans = oracle.dfa_find_iter(fwd, bwd, clean, 4)
+            c, s, en, panic = (int(x) for x in r)
+            assert c == cnt and not panic and (not cnt or (s, en) == spans[0]), (pat, form, h, clean, spans, r)
 
 
 def test_regex_unicode_classes_utf8():

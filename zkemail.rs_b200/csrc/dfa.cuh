@@ -14,24 +14,31 @@
 //
 // Mapping: one thread per (email, pattern); the pattern's forward and reverse tables live in
 // shared memory (copied once per CTA, 128-bit copies).  Per byte the work is a dependent chain of
-// two shared-memory loads (class, transition); throughput comes from occupancy.  Haystack bytes
-// are fetched 16 at a time (one LDG.128 per 16 bytes per lane) into registers.
+// shared-memory loads (one for DIRECT tables with 256-entry rows, two - class then transition - for
+// class-compressed tables); throughput comes from occupancy.  Haystack bytes are fetched 16 at a time
+// (one LDG.128 per 16 bytes per lane) into registers; the inner loop is unrolled over the block.
 #pragma once
 #include "common.cuh"
 
 namespace zkb {
 
 // Device table blob (built by the host from ZDF1, engine.cu: build_dfa_blob):
-//   u32[0]=n_states [1]=n_classes [2]=min_match*ncls [3]=max_match*ncls [4]=flags [5]=elem bytes
+//   u32[0]=n_states [1]=row stride (n_classes, or 256 for DIRECT tables) [2]=min_match*stride
+//   [3]=max_match*stride [4]=flags [5]=elem bytes [18]=1 for DIRECT tables
 //   u32[6..17] = start ids (premultiplied): unanchored[6], anchored[6]
-//   byte 128: class_map[256]; byte 384: start_map[256]; byte 640: trans (u16 or u32, premultiplied)
+//   byte 128: class_map[256]; byte 384: start_map[256]; byte 640: trans (u16 or u32, premultiplied by
+//   the row stride); DIRECT tables append eoi[n_states]
 #define ZKB_DFA_HDR 640
 #define ZKB_DFA_UTF8 2u
 #define ZKB_DFA_HAS_EMPTY 4u
 
-template <typename TT>
+// DIRECT tables have one 256-entry row per state (no byte-class indirection: one shared-memory load
+// per byte) followed by an end-of-input column eoi[n_states]; compressed tables index rows by byte
+// class (two dependent loads per byte) and keep the EOI transition as the last class.
+template <typename TT, bool DIRECT>
 struct DfaTab {
   const TT* trans;
+  const TT* eoi;
   const uint8_t* cmap;
   const uint8_t* smap;
   const uint32_t* hdr;
@@ -41,9 +48,16 @@ struct DfaTab {
     ncls = hdr[1]; min_m = hdr[2]; max_m = hdr[3]; flags = hdr[4];
     cmap = blob + 128; smap = blob + 384;
     trans = reinterpret_cast<const TT*>(blob + ZKB_DFA_HDR);
+    eoi = trans + (size_t)hdr[0] * 256;
   }
-  __device__ __forceinline__ uint32_t next(uint32_t sid, uint32_t byte) const { return trans[sid + cmap[byte]]; }
-  __device__ __forceinline__ uint32_t next_eoi(uint32_t sid) const { return trans[sid + ncls - 1]; }
+  __device__ __forceinline__ uint32_t next(uint32_t sid, uint32_t byte) const {
+    if (DIRECT) return trans[sid + byte];
+    return trans[sid + cmap[byte]];
+  }
+  __device__ __forceinline__ uint32_t next_eoi(uint32_t sid) const {
+    if (DIRECT) return eoi[sid >> 8];
+    return trans[sid + ncls - 1];
+  }
   // match ids form [min_m, max_m]; an empty range is encoded min_m > max_m
   __device__ __forceinline__ bool is_match(uint32_t sid) const { return sid >= min_m && sid <= max_m; }
   __device__ __forceinline__ uint32_t start(bool anchored, uint32_t kind) const { return hdr[6 + (anchored ? 6 : 0) + kind]; }
@@ -56,16 +70,23 @@ struct Cur {
   uint32_t c, o;
 };
 
-template <typename TT>
+template <typename TT, bool DIRECT>
 struct Searcher {
-  DfaTab<TT> f, r;
-  const uint8_t* h;
+  DfaTab<TT, DIRECT> f, r;
+  const uint8_t* h;   // 16-byte aligned; readable up to the next 16-byte boundary past n
   uint32_t n;
   bool qp;
-  uint32_t clen;  // cleaned length of the real bytes; known once a forward scan reached the end
+  uint32_t clen;      // cleaned length of the real bytes; known once a forward scan reached the end
+  uint4 win;          // register window: the 16-byte block win_blk of the haystack
+  uint32_t win_blk;
 
-  __device__ __forceinline__ uint32_t byte_at(uint32_t o) const { return h[o]; }
-  __device__ __forceinline__ void skip_soft(uint32_t& o) const {
+  __device__ __forceinline__ uint32_t byte_at(uint32_t o) {
+    const uint32_t blk = o >> 4;
+    if (blk != win_blk) { win = __ldg(reinterpret_cast<const uint4*>(h) + blk); win_blk = blk; }
+    const uint32_t w = (o & 8) ? ((o & 4) ? win.w : win.z) : ((o & 4) ? win.y : win.x);
+    return (w >> ((o & 3) * 8)) & 0xffu;
+  }
+  __device__ __forceinline__ void skip_soft(uint32_t& o) {
     if (qp)
       while (o + 2 < n && byte_at(o) == '=' && byte_at(o + 1) == '\r' && byte_at(o + 2) == '\n') o += 3;
   }
@@ -88,7 +109,7 @@ struct Searcher {
     return b;
   }
   // the cleaned byte just before p (requires p.c > 0); moves p back
-  __device__ __forceinline__ uint32_t back(Cur& p) const {
+  __device__ __forceinline__ uint32_t back(Cur& p) {
     p.c--;
     if (p.o >= n && p.c >= clen) return 0u;  // inside the zero padding
     uint32_t o = p.o - 1;
@@ -107,10 +128,38 @@ struct Searcher {
     bool have = false;
     Cur p = from;
     while (p.c < n) {
+      if ((p.o & 15u) == 0 && p.o + 16 <= n) {
+        // fast path: a whole 16-byte block from registers (one LDG.128 per 16 bytes per lane).  With
+        // soft-break removal on, blocks containing '=' take the byte-wise path below.
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(h + p.o));
+        bool plain = true;
+        if (qp) {
+          const uint32_t e = 0x3d3d3d3du;
+          const uint32_t x0 = v.x ^ e, x1 = v.y ^ e, x2 = v.z ^ e, x3 = v.w ^ e;
+          const uint32_t z = ((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | ((x2 - 0x01010101u) & ~x2) | ((x3 - 0x01010101u) & ~x3);
+          plain = (z & 0x80808080u) == 0;
+        }
+        if (plain) {
+          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 16; k++) {
+            const uint32_t b = (w4[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+            sid = f.next(sid, b);
+            if (sid <= f.max_m) {  // special states (dead, match) are numerically lowest
+              if (sid == 0) return have;
+              if (sid >= f.min_m) { have = true; end.c = p.c + k; end.o = p.o + k; end_byte = (int)b; }
+            }
+          }
+          p.c += 16; p.o += 16;
+          skip_soft(p.o);
+          if (p.o >= n) clen = p.c;
+          continue;
+        }
+      }
       Cur at = p;
       uint32_t b = take(p);
       sid = f.next(sid, b);
-      if (sid <= f.max_m) {  // special states (dead, match) are numerically lowest
+      if (sid <= f.max_m) {
         if (sid == 0) return have;
         if (sid >= f.min_m) { have = true; end = at; end_byte = (int)b; }
       }
@@ -120,7 +169,7 @@ struct Searcher {
     return have;
   }
   // find_rev: anchored, over cleaned [from.c, end.c); ms = leftmost start of a match ending at end
-  __device__ bool rev(Cur from, int prev_of_from, Cur end, int end_byte, uint32_t& ms) const {
+  __device__ bool rev(Cur from, int prev_of_from, Cur end, int end_byte, uint32_t& ms) {
     uint32_t sid = r.start(true, end_byte < 0 ? 2u : r.smap[end_byte]);
     if (sid == 0) return false;
     bool have = false;
@@ -162,6 +211,7 @@ struct Searcher {
   __device__ void run(uint32_t& count, uint32_t& fs, uint32_t& fe, bool& panic) {
     count = 0; fs = 0; fe = 0; panic = false;
     clen = 0xffffffffu;
+    win_blk = 0xffffffffu;
     Cur pos = begin();
     int prev = -1;
     uint32_t last_end = 0xffffffffu;
@@ -207,9 +257,9 @@ __device__ __forceinline__ void dfa_stage_tables(uint8_t* smem, const uint8_t* _
   }
 }
 
-template <typename TT>
+template <typename TT, bool DIRECT>
 __device__ __forceinline__ uint4 dfa_scan_one(const uint8_t* fb, const uint8_t* rb, const uint8_t* hay, uint32_t n, int qp) {
-  Searcher<TT> s;
+  Searcher<TT, DIRECT> s;
   s.f.init(fb); s.r.init(rb);
   s.h = hay; s.n = n; s.qp = qp != 0;
   uint32_t count, fs, fe; bool panic;
@@ -218,7 +268,7 @@ __device__ __forceinline__ uint4 dfa_scan_one(const uint8_t* fb, const uint8_t* 
 }
 
 // out[slot] = (match_count, first start, first end, reverse-search-failed flag)
-template <typename TT>
+template <typename TT, bool DIRECT>
 __global__ void __launch_bounds__(128)
 dfa_scan_kernel(const uint8_t* __restrict__ arena, const DfaItem* __restrict__ items,
                 uint32_t n_items, const uint8_t* __restrict__ fwd_blob, uint32_t fwd_bytes,
@@ -230,12 +280,12 @@ dfa_scan_kernel(const uint8_t* __restrict__ arena, const DfaItem* __restrict__ i
   uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_items) return;
   DfaItem it = items[idx];
-  out[it.out_slot] = dfa_scan_one<TT>(fb, rb, arena + it.hay_off, it.hay_len, qp);
+  out[it.out_slot] = dfa_scan_one<TT, DIRECT>(fb, rb, arena + it.hay_off, it.hay_len, qp);
 }
 
 // Engine form: items are interleaved per email (2*j = header preimage, 2*j+1 = canonical body);
 // `which` selects the haystack, the result of regex part `pi` of P goes to out[email * P + pi].
-template <typename TT>
+template <typename TT, bool DIRECT>
 __global__ void __launch_bounds__(128)
 dfa_scan_strided(const uint8_t* __restrict__ arena, const DfaItem* __restrict__ items, uint32_t n_emails,
                  uint32_t which, uint32_t P, uint32_t pi, const uint8_t* __restrict__ fwd_blob, uint32_t fwd_bytes,
@@ -247,7 +297,7 @@ dfa_scan_strided(const uint8_t* __restrict__ arena, const DfaItem* __restrict__ 
   uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_emails) return;
   DfaItem it = items[2 * idx + which];
-  out[(size_t)it.out_slot * P + pi] = dfa_scan_one<TT>(fb, rb, arena + it.hay_off, it.hay_len, qp);
+  out[(size_t)it.out_slot * P + pi] = dfa_scan_one<TT, DIRECT>(fb, rb, arena + it.hay_off, it.hay_len, qp);
 }
 
 }  // namespace zkb

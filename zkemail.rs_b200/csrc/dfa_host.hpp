@@ -44,35 +44,59 @@ inline bool zdf_parse(const uint8_t* b, size_t n, ZdfView& d) {
 }
 
 // ZDF1 -> device blob (see dfa.cuh).  elem = 2 when every premultiplied id fits in 16 bits.
-inline bool build_dfa_blob(const uint8_t* zdf, size_t len, bool want_reverse, std::vector<uint8_t>& blob,
-                           uint32_t& elem_bytes) {
+// direct = true expands the byte classes into 256-entry rows (+ an EOI column).
+inline bool build_dfa_blob(const uint8_t* zdf, size_t len, bool want_reverse, bool direct, uint32_t force_elem,
+                           std::vector<uint8_t>& blob, uint32_t& elem_bytes) {
   ZdfView d;
   if (!zdf_parse(zdf, len, d)) return false;
   if (((d.flags & 1u) != 0) != want_reverse) return false;
-  const uint64_t cells = (uint64_t)d.n_states * d.n_classes;
+  const uint32_t stride = direct ? 256u : d.n_classes;
+  const uint64_t cells = (uint64_t)d.n_states * stride;
   if (cells >= (1ull << 31)) return false;
-  elem_bytes = cells <= 65536 ? 2 : 4;
-  size_t bytes = ZKB_DFA_HDR + cells * elem_bytes;
+  elem_bytes = force_elem ? force_elem : (cells <= 65536 ? 2 : 4);
+  if (elem_bytes == 2 && cells > 65536) return false;
+  size_t bytes = ZKB_DFA_HDR + (cells + (direct ? d.n_states : 0)) * elem_bytes;
   blob.assign((bytes + 15) & ~(size_t)15, 0);
   uint32_t* hdr = reinterpret_cast<uint32_t*>(blob.data());
-  hdr[0] = d.n_states; hdr[1] = d.n_classes;
+  hdr[0] = d.n_states; hdr[1] = stride;
   if (d.min_match <= d.max_match && d.max_match < d.n_states) {
-    hdr[2] = d.min_match * d.n_classes; hdr[3] = d.max_match * d.n_classes;
+    hdr[2] = d.min_match * stride; hdr[3] = d.max_match * stride;
   } else {  // no match states
     hdr[2] = 1; hdr[3] = 0;
   }
   hdr[4] = d.flags; hdr[5] = elem_bytes;
-  for (int i = 0; i < 12; i++) hdr[6 + i] = d.start[i] * d.n_classes;
+  for (int i = 0; i < 12; i++) hdr[6 + i] = d.start[i] * stride;
+  hdr[18] = direct ? 1u : 0u;
   memcpy(blob.data() + 128, d.class_map, 256);
   memcpy(blob.data() + 384, d.start_map, 256);
-  if (elem_bytes == 2) {
-    uint16_t* t = reinterpret_cast<uint16_t*>(blob.data() + ZKB_DFA_HDR);
-    for (uint64_t i = 0; i < cells; i++) t[i] = (uint16_t)(rd32le(d.trans + 4 * i) * d.n_classes);
+  auto put = [&](uint64_t idx, uint32_t v) {
+    if (elem_bytes == 2) reinterpret_cast<uint16_t*>(blob.data() + ZKB_DFA_HDR)[idx] = (uint16_t)v;
+    else reinterpret_cast<uint32_t*>(blob.data() + ZKB_DFA_HDR)[idx] = v;
+  };
+  auto tr = [&](uint32_t s, uint32_t c) { return rd32le(d.trans + 4 * ((uint64_t)s * d.n_classes + c)) * stride; };
+  if (!direct) {
+    for (uint32_t s = 0; s < d.n_states; s++)
+      for (uint32_t c = 0; c < d.n_classes; c++) put((uint64_t)s * stride + c, tr(s, c));
   } else {
-    uint32_t* t = reinterpret_cast<uint32_t*>(blob.data() + ZKB_DFA_HDR);
-    for (uint64_t i = 0; i < cells; i++) t[i] = rd32le(d.trans + 4 * i) * d.n_classes;
+    for (uint32_t s = 0; s < d.n_states; s++) {
+      for (uint32_t b = 0; b < 256; b++) put((uint64_t)s * 256 + b, tr(s, d.class_map[b]));
+      put(cells + s, tr(s, d.n_classes - 1));
+    }
   }
   return true;
+}
+
+// Chooses the table form for a forward/reverse pair: DIRECT rows while both tables stay small enough
+// for >= 8 CTAs of shared memory per SM, one element width for both.
+inline bool build_dfa_pair(const uint8_t* fwd, size_t fwd_len, const uint8_t* bwd, size_t bwd_len,
+                           std::vector<uint8_t>& fb, std::vector<uint8_t>& rb, uint32_t& elem, bool& direct) {
+  ZdfView f, r;
+  if (!zdf_parse(fwd, fwd_len, f) || !zdf_parse(bwd, bwd_len, r)) return false;
+  direct = ((uint64_t)f.n_states + r.n_states) * 257 * 2 <= 24 * 1024;
+  const uint64_t fc = (uint64_t)f.n_states * (direct ? 256 : f.n_classes), rc = (uint64_t)r.n_states * (direct ? 256 : r.n_classes);
+  elem = (fc <= 65536 && rc <= 65536) ? 2 : 4;
+  uint32_t e1, e2;
+  return build_dfa_blob(fwd, fwd_len, false, direct, elem, fb, e1) && build_dfa_blob(bwd, bwd_len, true, direct, elem, rb, e2);
 }
 
 }  // namespace zkb

@@ -12,6 +12,10 @@
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define ZKB_HAVE_AVX2_DISPATCH 1
+#endif
 
 #include <string>
 #include <vector>
@@ -288,13 +292,16 @@ inline bool parse_usize_tag(const DkimSig& sig, const Tag* t, uint64_t& out) {
 }
 
 // ------------------------------------------------------------------ canonicalisation (single pass)
-// Relaxed body; out must hold n + 2 bytes.  Single pass with the state (o, prev_sp); 16-byte chunks
-// that the state machine would copy verbatim (no TAB, no SP followed by SP/CR, not ending in SP, not
-// starting with LF, and not directly after a SP) take an SSE2 fast path.
-inline size_t canon_body_relaxed(const uint8_t* in, size_t n, uint8_t* out) {
-  size_t o = 0, i = 0;
+// Relaxed body; out must hold n + 2 bytes (+32 bytes of slack for vector stores).  Single pass with
+// the state (o, prev_sp); chunks that the state machine would copy verbatim (no TAB, no SP followed
+// by SP/CR, not ending in SP, not starting with LF, and not directly after a SP) take a vector fast
+// path: 32 bytes per step with AVX2 (runtime dispatch), else 16 with SSE2.
+struct RelaxedBody {
+  const uint8_t* in;
+  uint8_t* out;
+  size_t n, o = 0, i = 0;
   bool prev_sp = false;
-  auto scalar = [&](size_t end) {
+  inline void scalar(size_t end) {
     for (; i < end; i++) {
       uint8_t c = in[i];
       if (c == ' ' || c == '\t') {
@@ -308,24 +315,50 @@ inline size_t canon_body_relaxed(const uint8_t* in, size_t n, uint8_t* out) {
       }
       out[o++] = c;
     }
-  };
+  }
+  inline size_t finish() {
+    scalar(n);
+    while (o >= 4 && out[o - 1] == '\n' && out[o - 2] == '\r' && out[o - 3] == '\n' && out[o - 4] == '\r') o -= 2;
+    if (o > 0 && !(o >= 2 && out[o - 2] == '\r' && out[o - 1] == '\n')) { out[o++] = '\r'; out[o++] = '\n'; }
+    return o;
+  }
+};
+#if defined(ZKB_HAVE_AVX2_DISPATCH)
+__attribute__((target("avx2"))) inline void relaxed_body_avx2(RelaxedBody& st) {
+  const __m256i vsp = _mm256_set1_epi8(' '), vtab = _mm256_set1_epi8('\t'), vcr = _mm256_set1_epi8('\r');
+  while (st.i + 32 <= st.n) {
+    __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(st.in + st.i));
+    uint32_t sp = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, vsp));
+    uint32_t tab = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, vtab));
+    uint32_t cr = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, vcr));
+    uint32_t bad = tab | (sp & ((sp | cr) >> 1)) | (sp & 0x80000000u);
+    if (bad | (uint32_t)st.prev_sp | (uint32_t)(st.in[st.i] == '\n')) { st.scalar(st.i + 32); continue; }
+    _mm256_storeu_si256(reinterpret_cast<__m256i*>(st.out + st.o), v);
+    st.o += 32; st.i += 32;
+  }
+}
+inline bool cpu_has_avx2() { static const bool v = __builtin_cpu_supports("avx2"); return v; }
+#endif
+inline size_t canon_body_relaxed(const uint8_t* in, size_t n, uint8_t* out) {
+  RelaxedBody st;
+  st.in = in; st.out = out; st.n = n;
+#if defined(ZKB_HAVE_AVX2_DISPATCH)
+  if (cpu_has_avx2()) { relaxed_body_avx2(st); return st.finish(); }
+#endif
 #if defined(__SSE2__)
   const __m128i vsp = _mm_set1_epi8(' '), vtab = _mm_set1_epi8('\t'), vcr = _mm_set1_epi8('\r');
-  while (i + 16 <= n) {
-    __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(in + i));
+  while (st.i + 16 <= n) {
+    __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(in + st.i));
     unsigned sp = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(v, vsp));
     unsigned tab = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(v, vtab));
     unsigned cr = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(v, vcr));
     unsigned bad = tab | (sp & ((sp | cr) >> 1)) | (sp & 0x8000u);
-    if (bad | (unsigned)prev_sp | (unsigned)(in[i] == '\n')) { scalar(i + 16); continue; }
-    _mm_storeu_si128(reinterpret_cast<__m128i*>(out + o), v);
-    o += 16; i += 16;
+    if (bad | (unsigned)st.prev_sp | (unsigned)(in[st.i] == '\n')) { st.scalar(st.i + 16); continue; }
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(out + st.o), v);
+    st.o += 16; st.i += 16;
   }
 #endif
-  scalar(n);
-  while (o >= 4 && out[o - 1] == '\n' && out[o - 2] == '\r' && out[o - 3] == '\n' && out[o - 4] == '\r') o -= 2;
-  if (o > 0 && !(o >= 2 && out[o - 2] == '\r' && out[o - 1] == '\n')) { out[o++] = '\r'; out[o++] = '\n'; }
-  return o;
+  return st.finish();
 }
 inline size_t canon_body_simple(const uint8_t* in, size_t n, uint8_t* out) {
   if (n == 0) { out[0] = '\r'; out[1] = '\n'; return 2; }
@@ -347,26 +380,67 @@ inline size_t put_key(const uint8_t* key, size_t klen, uint8_t* out, bool lower)
   }
   return o;
 }
-// out must hold 2*klen + vlen + 3
-inline size_t canon_header_relaxed(const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen, uint8_t* out) {
-  while (klen > 0 && latin1_ws(key[klen - 1])) klen--;
-  size_t o = put_key(key, klen, out, true);
-  out[o++] = ':';
-  size_t start = o;
-  bool prev_sp = true;  // swallows leading SP
-  for (size_t i = 0; i < vlen; i++) {
-    uint8_t c = val[i];
-    if (c == '\r' && i + 1 < vlen && val[i + 1] == '\n') { i++; continue; }
+// Relaxed header value, streamed over one or more input segments (the b= blanking of the
+// DKIM-Signature header yields two): TAB->SP, every CRLF removed, SP runs collapsed, leading and
+// trailing SP dropped.  A CR at the end of one segment and a LF at the start of the next form a
+// CRLF, exactly as if the segments had been concatenated first.
+struct RelaxedValue {
+  uint8_t* out;
+  size_t o, start;
+  bool prev_sp = true;     // swallows leading SP
+  bool pending_cr = false;
+  explicit RelaxedValue(uint8_t* dst, size_t at) : out(dst), o(at), start(at) {}
+  inline void put(uint8_t c) {
     if (c == ' ' || c == '\t') {
       if (!prev_sp) { out[o++] = ' '; prev_sp = true; }
-      continue;
+      return;
     }
     prev_sp = false;
     out[o++] = c;
   }
-  if (o > start && out[o - 1] == ' ') o--;
-  out[o++] = '\r'; out[o++] = '\n';
-  return o;
+  void feed(const uint8_t* v, size_t n) {
+    size_t i = 0;
+    if (pending_cr && n) {
+      pending_cr = false;
+      if (v[0] == '\n') i = 1; else put('\r');
+    }
+    while (i < n) {
+#if defined(__SSE2__)
+      if (i + 16 <= n && !prev_sp) {
+        __m128i x = _mm_loadu_si128(reinterpret_cast<const __m128i*>(v + i));
+        unsigned sp = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(x, _mm_set1_epi8(' ')));
+        unsigned bad = (unsigned)_mm_movemask_epi8(_mm_or_si128(_mm_cmpeq_epi8(x, _mm_set1_epi8('\t')), _mm_cmpeq_epi8(x, _mm_set1_epi8('\r'))));
+        if (!(bad | (sp & (sp >> 1)) | (sp & 0x8000u))) {
+          _mm_storeu_si128(reinterpret_cast<__m128i*>(out + o), x);
+          o += 16; i += 16;
+          continue;
+        }
+      }
+#endif
+      uint8_t c = v[i];
+      if (c == '\r') {
+        if (i + 1 < n) { if (v[i + 1] == '\n') { i += 2; continue; } }
+        else { pending_cr = true; i++; continue; }
+      }
+      put(c);
+      i++;
+    }
+  }
+  size_t finish() {
+    if (pending_cr) { pending_cr = false; put('\r'); }
+    if (o > start && out[o - 1] == ' ') o--;
+    out[o++] = '\r'; out[o++] = '\n';
+    return o;
+  }
+};
+// out must hold 2*klen + vlen + 3 (+16 bytes of slack for the vector stores)
+inline size_t canon_header_relaxed(const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen, uint8_t* out) {
+  while (klen > 0 && latin1_ws(key[klen - 1])) klen--;
+  size_t o = put_key(key, klen, out, true);
+  out[o++] = ':';
+  RelaxedValue rv(out, o);
+  rv.feed(val, vlen);
+  return rv.finish();
 }
 inline size_t canon_header_simple(const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen, uint8_t* out) {
   size_t o = put_key(key, klen, out, false);
@@ -377,7 +451,7 @@ inline size_t canon_header_simple(const uint8_t* key, size_t klen, const uint8_t
 }
 
 // Upper bound of the header-hash preimage for a message whose header block is `hdr_bytes` long.
-inline size_t preimage_bound(size_t hdr_bytes, size_t sig_val_len) { return 2 * hdr_bytes + 3 * sig_val_len + 64; }
+inline size_t preimage_bound(size_t hdr_bytes, size_t sig_val_len) { return 2 * hdr_bytes + 3 * sig_val_len + 96; }
 
 // select_headers + canonicalise + the b-less DKIM-Signature (no trailing CRLF). Returns length.
 inline size_t build_header_preimage(const uint8_t* raw, const std::vector<HeaderField>& hs, const DkimSig& sig,
@@ -419,30 +493,43 @@ inline size_t build_header_preimage(const uint8_t* raw, const std::vector<Header
     }
   }
   // the signature header with every occurrence of the raw b= text removed
+  // (value.replace(raw_b, ""): non-overlapping, left to right), canonicalised, final CRLF dropped
   const Tag* tb = sig.get("b");
   const uint8_t* v = sig.s;
-  size_t vl = sig.n;
-  if (tb->raw_len != 0) {
-    // value.replace(raw_b, ""): every (non-overlapping, left to right) occurrence of the raw b= text
-    scratch.clear();
-    const uint8_t* pat = sig.s + tb->raw_off;
-    const size_t pl = tb->raw_len;
+  const size_t vl = sig.n;
+  const uint8_t* pat = sig.s + tb->raw_off;
+  const size_t pl = tb->raw_len;
+  if (relaxed) {
+    memcpy(out + o, "dkim-signature:", 15);
+    RelaxedValue rv(out, o + 15);
     size_t i = 0, copied = 0;
-    while (i + pl <= vl) {
-      const uint8_t* f = (const uint8_t*)memchr(sig.s + i, pat[0], vl - pl - i + 1);
-      if (!f) break;
-      i = (size_t)(f - sig.s);
-      if (memcmp(f, pat, pl) == 0) {
-        scratch.append((const char*)sig.s + copied, i - copied);
-        i += pl;
-        copied = i;
-      } else i++;
+    if (pl) {
+      while (i + pl <= vl) {
+        const uint8_t* f = (const uint8_t*)memchr(v + i, pat[0], vl - pl - i + 1);
+        if (!f) break;
+        i = (size_t)(f - v);
+        if (memcmp(f, pat, pl) == 0) { rv.feed(v + copied, i - copied); i += pl; copied = i; }
+        else i++;
+      }
     }
-    scratch.append((const char*)sig.s + copied, vl - copied);
-    v = (const uint8_t*)scratch.data(); vl = scratch.size();
+    rv.feed(v + copied, vl - copied);
+    return rv.finish() - 2;
   }
-  size_t w = relaxed ? canon_header_relaxed((const uint8_t*)"DKIM-Signature", 14, v, vl, out + o)
-                     : canon_header_simple((const uint8_t*)"DKIM-Signature", 14, v, vl, out + o);
+  scratch.clear();
+  {
+    size_t i = 0, copied = 0;
+    if (pl) {
+      while (i + pl <= vl) {
+        const uint8_t* f = (const uint8_t*)memchr(v + i, pat[0], vl - pl - i + 1);
+        if (!f) break;
+        i = (size_t)(f - v);
+        if (memcmp(f, pat, pl) == 0) { scratch.append((const char*)v + copied, i - copied); i += pl; copied = i; }
+        else i++;
+      }
+    }
+    scratch.append((const char*)v + copied, vl - copied);
+  }
+  size_t w = canon_header_simple((const uint8_t*)"DKIM-Signature", 14, (const uint8_t*)scratch.data(), scratch.size(), out + o);
   return o + w - 2;
 }
 
@@ -463,35 +550,47 @@ inline const uint8_t* find_body(const uint8_t* raw, size_t n, size_t& blen, size
 // ------------------------------------------------------------------ base64 (STANDARD, strict)
 struct B64 {
   int8_t t[256];
+  uint32_t d0[256], d1[256], d2[256], d3[256];  // pre-shifted values; 0x01000000 flags an invalid char
   B64() {
     memset(t, -1, sizeof t);
     const char* a = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
     for (int i = 0; i < 64; i++) t[(uint8_t)a[i]] = (int8_t)i;
+    for (int c = 0; c < 256; c++) {
+      if (t[c] < 0) { d0[c] = d1[c] = d2[c] = d3[c] = 0x01000000u; continue; }
+      uint32_t v = (uint32_t)t[c];
+      d0[c] = v << 18; d1[c] = v << 12; d2[c] = v << 6; d3[c] = v;
+    }
   }
 };
 inline const B64& b64tab() { static const B64 t; return t; }
 // returns decoded length or -1.  out needs 3*n/4 bytes.
 inline long base64_decode(const uint8_t* in, size_t n, uint8_t* out) {
   if (n % 4) return -1;
-  const int8_t* T = b64tab().t;
-  size_t o = 0;
-  for (size_t i = 0; i < n; i += 4) {
+  const B64& B = b64tab();
+  const int8_t* T = B.t;
+  size_t o = 0, i = 0;
+  for (; i + 4 < n; i += 4) {  // all quads but the last cannot carry padding
+    uint32_t v = B.d0[in[i]] | B.d1[in[i + 1]] | B.d2[in[i + 2]] | B.d3[in[i + 3]];
+    if (v & 0x01000000u) return -1;
+    out[o++] = (uint8_t)(v >> 16); out[o++] = (uint8_t)(v >> 8); out[o++] = (uint8_t)v;
+  }
+  if (i < n) {
     int a = T[in[i]], b = T[in[i + 1]], c = T[in[i + 2]], d = T[in[i + 3]];
     if ((a | b | c | d) >= 0) {
       out[o++] = (uint8_t)((a << 2) | (b >> 4));
       out[o++] = (uint8_t)((b << 4) | (c >> 2));
       out[o++] = (uint8_t)((c << 6) | d);
-      continue;
+    } else {
+      if (a < 0 || b < 0) return -1;
+      if (in[i + 2] == '=' && in[i + 3] == '=') {
+        if (b & 15) return -1;
+        out[o++] = (uint8_t)((a << 2) | (b >> 4));
+      } else if (in[i + 3] == '=' && c >= 0) {
+        if (c & 3) return -1;
+        out[o++] = (uint8_t)((a << 2) | (b >> 4));
+        out[o++] = (uint8_t)((b << 4) | (c >> 2));
+      } else return -1;
     }
-    if (i + 4 != n || a < 0 || b < 0) return -1;
-    if (in[i + 2] == '=' && in[i + 3] == '=') {
-      if (b & 15) return -1;
-      out[o++] = (uint8_t)((a << 2) | (b >> 4));
-    } else if (in[i + 3] == '=' && c >= 0) {
-      if (c & 3) return -1;
-      out[o++] = (uint8_t)((a << 2) | (b >> 4));
-      out[o++] = (uint8_t)((b << 4) | (c >> 2));
-    } else return -1;
   }
   return (long)o;
 }

@@ -248,7 +248,7 @@ struct zkb_regex_set {
   zkb_engine* eng = nullptr;
   size_t n_header = 0, n_body = 0;
   int header_present = 0, body_present = 0;
-  struct Part { uint8_t* d_fwd = nullptr; uint8_t* d_rev = nullptr; uint32_t fwd_bytes = 0, rev_bytes = 0, elem = 2; bool body = false; };
+  struct Part { uint8_t* d_fwd = nullptr; uint8_t* d_rev = nullptr; uint32_t fwd_bytes = 0, rev_bytes = 0, elem = 2; bool body = false, direct = false; };
   std::vector<Part> parts;
   size_t n_active() const { return (header_present ? n_header : 0) + (body_present ? n_body : 0); }
 };
@@ -760,7 +760,7 @@ int launch_chunk(zkb_engine* e, const DeviceChunk& d, const zkb_regex_set* rs, c
       const zkb_regex_set::Part& part = rs->parts[p];
       if (part.body ? !rs->body_present : !rs->header_present) continue;
       // items are interleaved (header, body) per email; out slot = email * P + pi
-      launch_dfa_strided(part.elem, d.arena.p, d.dfa_items, d.n_dfa, part.body ? 1u : 0u, (uint32_t)d.P, (uint32_t)pi, part.d_fwd,
+      launch_dfa_strided(part.elem, part.direct, d.arena.p, d.dfa_items, d.n_dfa, part.body ? 1u : 0u, (uint32_t)d.P, (uint32_t)pi, part.d_fwd,
                          part.fwd_bytes, part.d_rev, part.rev_bytes, e->smem_optin, part.body ? 1 : 0, d.dfa_out, s);
       nl++; pi++;
     }
@@ -971,25 +971,16 @@ int zkb_regex_set_create(zkb_engine* e, const zkb_dfa_view* parts, size_t n_head
   rs->header_present = header_present; rs->body_present = body_present;
   for (size_t p = 0; p < n_header + n_body; p++) {
     std::vector<uint8_t> fb, rb;
-    uint32_t fe = 2, re = 2;
-    if (!build_dfa_blob(parts[p].fwd, parts[p].fwd_len, false, fb, fe) || !build_dfa_blob(parts[p].bwd, parts[p].bwd_len, true, rb, re)) {
+    uint32_t fe = 2;
+    bool direct = false;
+    if (!build_dfa_pair(parts[p].fwd, parts[p].fwd_len, parts[p].bwd, parts[p].bwd_len, fb, rb, fe, direct)) {
       zkb_regex_set_destroy(rs);
       return ZKB_E_REGEX;
-    }
-    if (fe != re) {  // the kernel is instantiated for one element width: widen the narrow table
-      std::vector<uint8_t>& nb = fe == 2 ? fb : rb;
-      const uint32_t* h = (const uint32_t*)nb.data();
-      size_t cells = (size_t)h[0] * h[1];
-      std::vector<uint8_t> w((ZKB_DFA_HDR + cells * 4 + 15) & ~(size_t)15, 0);
-      memcpy(w.data(), nb.data(), ZKB_DFA_HDR);
-      ((uint32_t*)w.data())[5] = 4;
-      for (size_t i = 0; i < cells; i++) ((uint32_t*)(w.data() + ZKB_DFA_HDR))[i] = ((const uint16_t*)(nb.data() + ZKB_DFA_HDR))[i];
-      nb.swap(w);
-      fe = re = 4;
     }
     zkb_regex_set::Part part;
     part.body = p >= n_header;
     part.elem = fe;
+    part.direct = direct;
     part.fwd_bytes = (uint32_t)fb.size(); part.rev_bytes = (uint32_t)rb.size();
     if (cudaMalloc((void**)&part.d_fwd, fb.size()) != cudaSuccess || cudaMalloc((void**)&part.d_rev, rb.size()) != cudaSuccess) {
       zkb_regex_set_destroy(rs);
@@ -1009,6 +1000,20 @@ void zkb_regex_set_destroy(zkb_regex_set* s) {
   delete s;
 }
 
+// Chunk boundaries: at most `max_emails` emails and about `max_bytes` raw bytes per chunk, so that
+// large-body batches still pipeline (H2D of chunk k overlaps the host pack of chunk k+1).
+static std::vector<size_t> chunk_bounds(const zkb_email_view* emails, size_t n, size_t max_emails, size_t max_bytes) {
+  std::vector<size_t> b;
+  b.push_back(0);
+  size_t cnt = 0, bytes = 0;
+  for (size_t i = 0; i < n; i++) {
+    cnt++; bytes += emails[i].raw_email_len;
+    if (cnt >= max_emails || bytes >= max_bytes) { b.push_back(i + 1); cnt = 0; bytes = 0; }
+  }
+  if (b.back() != n) b.push_back(n);
+  return b;
+}
+
 static double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -1020,8 +1025,8 @@ int zkb_verify_batch(zkb_engine* e, const zkb_email_view* emails, size_t n, cons
   if (regex && regex->eng != e) return ZKB_E_INVALID;
   std::lock_guard<std::mutex> lock(e->run_mu);
   CK(cudaSetDevice(e->device));
-  const size_t CE = e->chunk_emails;
-  const size_t nchunks = (n + CE - 1) / CE;
+  const std::vector<size_t> bounds = chunk_bounds(emails, n, e->chunk_emails, (size_t)192 << 20);
+  const size_t nchunks = bounds.size() - 1;
   Chunk chunks[3];
   bool busy[3] = {false, false, false};
   const size_t P = regex ? regex->n_active() : 0;
@@ -1049,7 +1054,7 @@ int zkb_verify_batch(zkb_engine* e, const zkb_email_view* emails, size_t n, cons
     if (rc) break;
     Slot& s = e->slots[si];
     Chunk& ch = chunks[si];
-    size_t e0 = k * CE, ne = std::min(CE, n - e0);
+    size_t e0 = bounds[k], ne = bounds[k + 1] - bounds[k];
     double t0 = now_s();
     rc = pack_chunk(e, emails, e0, ne, regex, ch, s.meta);
     if (rc) break;
@@ -1107,14 +1112,15 @@ int zkb_batch_prepare(zkb_engine* e, const zkb_email_view* emails, size_t n, con
   CK(cudaSetDevice(e->device));
   zkb_batch* b = new zkb_batch();
   b->eng = e; b->regex = regex; b->n = n; b->emails = emails; b->captures = captures;
-  const size_t CE = e->chunk_emails * 8;  // resident batches: fewer, larger launches
+  // resident batches: fewer, larger launches (better SM balance; nothing to overlap with)
+  const std::vector<size_t> bounds = chunk_bounds(emails, n, e->chunk_emails * 8, (size_t)3 << 30);
   cudaStream_t s = e->slots[0].stream;
   int rc = ZKB_OK;
-  for (size_t e0 = 0; e0 < n && rc == ZKB_OK; e0 += CE) {
+  for (size_t k = 0; k + 1 < bounds.size() && rc == ZKB_OK; k++) {
     Chunk* ch = new Chunk();
     DeviceChunk* d = new DeviceChunk();
     b->chunks.push_back(ch); b->dev.push_back(d);
-    rc = pack_chunk(e, emails, e0, std::min(CE, n - e0), regex, *ch, e->slots[0].meta);
+    rc = pack_chunk(e, emails, bounds[k], bounds[k + 1] - bounds[k], regex, *ch, e->slots[0].meta);
     if (rc) break;
     rc = sync_keytab(e, s);
     if (rc) break;
@@ -1387,7 +1393,7 @@ int zkb_dfa_scan_batch(zkb_engine* e, const zkb_dfa_view* part, const uint8_t* d
   CK(cudaMemset(d_out, 0, n * 16));
   const zkb_regex_set::Part& p = rs->parts[0];
   cudaStream_t s = e->slots[0].stream;
-  launch_dfa(p.elem, d_arena, d_items, (uint32_t)n, p.d_fwd, p.fwd_bytes, p.d_rev, p.rev_bytes, e->smem_optin, qp, d_out, s);
+  launch_dfa(p.elem, p.direct, d_arena, d_items, (uint32_t)n, p.d_fwd, p.fwd_bytes, p.d_rev, p.rev_bytes, e->smem_optin, qp, d_out, s);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s));
   CK(cudaMemcpy(out, d_out, n * 16, cudaMemcpyDeviceToHost));
