@@ -102,9 +102,11 @@ int emu_dfa_scan(const uint8_t* fwd, size_t fl, const uint8_t* bwd, size_t bl, c
   for (uint32_t i = 0; i < n; i++) { items[i].hay_off = off[i]; items[i].hay_len = len[i]; items[i].out_slot = i; }
   const unsigned block = 128;
   emu::launch((n + block - 1) / block, block, [&]() {
-#define RUN(TT, D) dfa_scan_kernel<TT, D>(arena, items.data(), n, fb.data(), (uint32_t)fb.size(), rb.data(), (uint32_t)rb.size(), use_smem, qp, (uint4*)out)
+#define RUN1(TT, D, S) dfa_scan_kernel<TT, D, S>(arena, items.data(), n, fb.data(), (uint32_t)fb.size(), rb.data(), (uint32_t)rb.size(), qp, (uint4*)out)
+#define RUN(TT, D) do { if (use_smem) RUN1(TT, D, true); else RUN1(TT, D, false); } while (0)
     if (elem == 2) { if (direct) RUN(uint16_t, true); else RUN(uint16_t, false); }
     else { if (direct) RUN(uint32_t, true); else RUN(uint32_t, false); }
+#undef RUN1
 #undef RUN
   });
   return 0;

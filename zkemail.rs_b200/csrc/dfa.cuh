@@ -127,43 +127,49 @@ struct Searcher {
     if (sid == 0) return false;
     bool have = false;
     Cur p = from;
-    while (p.c < n) {
-      if ((p.o & 15u) == 0 && p.o + 16 <= n) {
-        // fast path: a whole 16-byte block from registers (one LDG.128 per 16 bytes per lane).  With
-        // soft-break removal on, blocks containing '=' take the byte-wise path below.
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(h + p.o));
-        bool plain = true;
+    // Single-exit loop (no return inside) so that the lanes of a warp reconverge every iteration.
+    while (p.c < n && sid != 0) {
+      bool block = (p.o & 15u) == 0 && p.o + 16 <= n;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (block) {
+        // a whole 16-byte block from registers (one LDG.128 per 16 bytes per lane).  With soft-break
+        // removal on, blocks containing '=' take the byte-wise path below.
+        v = __ldg(reinterpret_cast<const uint4*>(h + p.o));
         if (qp) {
           const uint32_t e = 0x3d3d3d3du;
           const uint32_t x0 = v.x ^ e, x1 = v.y ^ e, x2 = v.z ^ e, x3 = v.w ^ e;
           const uint32_t z = ((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | ((x2 - 0x01010101u) & ~x2) | ((x3 - 0x01010101u) & ~x3);
-          plain = (z & 0x80808080u) == 0;
-        }
-        if (plain) {
-          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int k = 0; k < 16; k++) {
-            const uint32_t b = (w4[k >> 2] >> ((k & 3) * 8)) & 0xffu;
-            sid = f.next(sid, b);
-            if (sid <= f.max_m) {  // special states (dead, match) are numerically lowest
-              if (sid == 0) return have;
-              if (sid >= f.min_m) { have = true; end.c = p.c + k; end.o = p.o + k; end_byte = (int)b; }
-            }
-          }
-          p.c += 16; p.o += 16;
-          skip_soft(p.o);
-          if (p.o >= n) clen = p.c;
-          continue;
+          block = (z & 0x80808080u) == 0;
         }
       }
-      Cur at = p;
-      uint32_t b = take(p);
-      sid = f.next(sid, b);
-      if (sid <= f.max_m) {
-        if (sid == 0) return have;
-        if (sid >= f.min_m) { have = true; end = at; end_byte = (int)b; }
+      if (block) {
+        // Branch-free over the block: lanes must not split on per-byte events.  The dead state is
+        // absorbing (row 0 is all zeros) and never a match, so finishing the block after dying is
+        // harmless; the last match position inside the block is kept in mk.
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+        int mk = -1;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          const uint32_t b = (w4[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+          sid = f.next(sid, b);
+          mk = (sid >= f.min_m && sid <= f.max_m) ? k : mk;
+        }
+        if (mk >= 0) {
+          have = true; end.c = p.c + (uint32_t)mk; end.o = p.o + (uint32_t)mk;
+          const uint32_t w = (mk & 8) ? ((mk & 4) ? v.w : v.z) : ((mk & 4) ? v.y : v.x);
+          end_byte = (int)((w >> ((mk & 3) * 8)) & 0xffu);
+        }
+        p.c += 16; p.o += 16;
+        skip_soft(p.o);
+        if (p.o >= n) clen = p.c;
+      } else {
+        Cur at = p;
+        uint32_t b = take(p);
+        sid = f.next(sid, b);
+        if (sid >= f.min_m && sid <= f.max_m) { have = true; end = at; end_byte = (int)b; }
       }
     }
+    if (sid == 0) return have;  // dead: the search ends with the last recorded match
     sid = f.next_eoi(sid);
     if (f.is_match(sid)) { have = true; end = p; end_byte = -1; }
     return have;
@@ -174,14 +180,12 @@ struct Searcher {
     if (sid == 0) return false;
     bool have = false;
     Cur p = end;
-    while (p.c > from.c) {
+    while (p.c > from.c && sid != 0) {
       uint32_t b = back(p);
       sid = r.next(sid, b);
-      if (sid <= r.max_m) {
-        if (sid == 0) return have;
-        if (sid >= r.min_m) { have = true; ms = p.c + 1; }
-      }
+      if (sid >= r.min_m && sid <= r.max_m) { have = true; ms = p.c + 1; }
     }
+    if (sid == 0) return have;
     sid = prev_of_from < 0 ? r.next_eoi(sid) : r.next(sid, (uint32_t)prev_of_from);
     if (r.is_match(sid)) { have = true; ms = from.c; }
     return have;
@@ -241,19 +245,23 @@ struct Searcher {
 #define ZKB_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
 #endif
 
-// Copies both tables into shared memory (when they fit) and returns the pointers to scan from.
+// Copies both tables into shared memory (SMEM instantiations; 128-bit copies, blobs are 16-byte padded
+// by the host).  SMEM is a template parameter so that the table pointers are derived unconditionally
+// from the shared array and the scan uses LDS rather than generic loads.
+template <bool SMEM>
 __device__ __forceinline__ void dfa_stage_tables(uint8_t* smem, const uint8_t* __restrict__ fwd_blob, uint32_t fwd_bytes,
-                                                 const uint8_t* __restrict__ rev_blob, uint32_t rev_bytes, int use_smem,
+                                                 const uint8_t* __restrict__ rev_blob, uint32_t rev_bytes,
                                                  const uint8_t*& fb, const uint8_t*& rb) {
-  fb = fwd_blob; rb = rev_blob;
-  if (use_smem) {  // blobs are 16-byte padded by the host
-    uint32_t fpad = (fwd_bytes + 15u) & ~15u, rpad = (rev_bytes + 15u) & ~15u;
+  if (SMEM) {
+    const uint32_t fpad = (fwd_bytes + 15u) & ~15u, rpad = (rev_bytes + 15u) & ~15u;
     for (uint32_t i = threadIdx.x * 16; i < fpad; i += blockDim.x * 16)
       *reinterpret_cast<uint4*>(smem + i) = *reinterpret_cast<const uint4*>(fwd_blob + i);
     for (uint32_t i = threadIdx.x * 16; i < rpad; i += blockDim.x * 16)
       *reinterpret_cast<uint4*>(smem + fpad + i) = *reinterpret_cast<const uint4*>(rev_blob + i);
     __syncthreads();
     fb = smem; rb = smem + fpad;
+  } else {
+    fb = fwd_blob; rb = rev_blob;
   }
 }
 
@@ -268,15 +276,15 @@ __device__ __forceinline__ uint4 dfa_scan_one(const uint8_t* fb, const uint8_t* 
 }
 
 // out[slot] = (match_count, first start, first end, reverse-search-failed flag)
-template <typename TT, bool DIRECT>
+template <typename TT, bool DIRECT, bool SMEM>
 __global__ void __launch_bounds__(128)
 dfa_scan_kernel(const uint8_t* __restrict__ arena, const DfaItem* __restrict__ items,
                 uint32_t n_items, const uint8_t* __restrict__ fwd_blob, uint32_t fwd_bytes,
-                const uint8_t* __restrict__ rev_blob, uint32_t rev_bytes, int use_smem, int qp,
+                const uint8_t* __restrict__ rev_blob, uint32_t rev_bytes, int qp,
                 uint4* __restrict__ out) {
   ZKB_DYN_SMEM(smem);
   const uint8_t *fb, *rb;
-  dfa_stage_tables(smem, fwd_blob, fwd_bytes, rev_blob, rev_bytes, use_smem, fb, rb);
+  dfa_stage_tables<SMEM>(smem, fwd_blob, fwd_bytes, rev_blob, rev_bytes, fb, rb);
   uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_items) return;
   DfaItem it = items[idx];
@@ -285,15 +293,15 @@ dfa_scan_kernel(const uint8_t* __restrict__ arena, const DfaItem* __restrict__ i
 
 // Engine form: items are interleaved per email (2*j = header preimage, 2*j+1 = canonical body);
 // `which` selects the haystack, the result of regex part `pi` of P goes to out[email * P + pi].
-template <typename TT, bool DIRECT>
+template <typename TT, bool DIRECT, bool SMEM>
 __global__ void __launch_bounds__(128)
 dfa_scan_strided(const uint8_t* __restrict__ arena, const DfaItem* __restrict__ items, uint32_t n_emails,
                  uint32_t which, uint32_t P, uint32_t pi, const uint8_t* __restrict__ fwd_blob, uint32_t fwd_bytes,
-                 const uint8_t* __restrict__ rev_blob, uint32_t rev_bytes, int use_smem, int qp,
+                 const uint8_t* __restrict__ rev_blob, uint32_t rev_bytes, int qp,
                  uint4* __restrict__ out) {
   ZKB_DYN_SMEM(smem);
   const uint8_t *fb, *rb;
-  dfa_stage_tables(smem, fwd_blob, fwd_bytes, rev_blob, rev_bytes, use_smem, fb, rb);
+  dfa_stage_tables<SMEM>(smem, fwd_blob, fwd_bytes, rev_blob, rev_bytes, fb, rb);
   uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_emails) return;
   DfaItem it = items[2 * idx + which];

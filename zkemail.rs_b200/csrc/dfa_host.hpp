@@ -73,7 +73,9 @@ inline bool build_dfa_blob(const uint8_t* zdf, size_t len, bool want_reverse, bo
     if (elem_bytes == 2) reinterpret_cast<uint16_t*>(blob.data() + ZKB_DFA_HDR)[idx] = (uint16_t)v;
     else reinterpret_cast<uint32_t*>(blob.data() + ZKB_DFA_HDR)[idx] = v;
   };
-  auto tr = [&](uint32_t s, uint32_t c) { return rd32le(d.trans + 4 * ((uint64_t)s * d.n_classes + c)) * stride; };
+  // state 0 is the dead state: the search stops there and its transitions are never consulted by the
+  // reference algorithm; the kernel relies on it being absorbing, so its row is forced to zeros
+  auto tr = [&](uint32_t s, uint32_t c) { return s == 0 ? 0u : rd32le(d.trans + 4 * ((uint64_t)s * d.n_classes + c)) * stride; };
   if (!direct) {
     for (uint32_t s = 0; s < d.n_states; s++)
       for (uint32_t c = 0; c < d.n_classes; c++) put((uint64_t)s * stride + c, tr(s, c));
