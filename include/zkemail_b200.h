@@ -162,6 +162,12 @@ int zkb_batch_get_stats(const zkb_batch *b, zkb_batch_stats *out);
  * the engine stream: [0]=sha256 [1]=rsa [2]=dfa [3]=bh/finalize [4]=whole run */
 int zkb_batch_last_timing(const zkb_batch *b, float ms[5]);
 void *zkb_engine_stream(zkb_engine *e);          /* cudaStream_t of the engine */
+/* Device-resident verdict words of chunk `chunk` of a prepared batch (one u32 per signature candidate:
+ * bit0 = RSA ok, bit1 = bh= ok), for the multi-GPU all-gather of verdict bits over NCCL without a
+ * host round trip.  *n_chunks (optional) receives the number of chunks.  Valid until the batch is
+ * destroyed; written by zkb_batch_run*. */
+int zkb_batch_device_flags(const zkb_batch *b, size_t chunk, void **flags, size_t *n_flags,
+                           size_t *n_chunks);
 
 /* ---- regex compiler (stands in for helpers/src/regex.rs:7-51, which needs regex-automata) ----
  * Compiles `pattern` (Rust-regex syntax subset, Unicode/UTF-8 mode as DFARegex::new) to forward

@@ -1205,6 +1205,15 @@ int zkb_batch_get_stats(const zkb_batch* b, zkb_batch_stats* out) {
   return ZKB_OK;
 }
 
+int zkb_batch_device_flags(const zkb_batch* b, size_t chunk, void** flags, size_t* n_flags, size_t* n_chunks) {
+  if (!b) return ZKB_E_INVALID;
+  if (n_chunks) *n_chunks = b->dev.size();
+  if (chunk >= b->dev.size()) return flags ? ZKB_E_INVALID : ZKB_OK;
+  if (flags) *flags = b->dev[chunk]->cand_flags;
+  if (n_flags) *n_flags = b->dev[chunk]->C;
+  return ZKB_OK;
+}
+
 int zkb_batch_fetch(zkb_batch* b, zkb_result* out) {
   if (!b || (!out && b->n)) return ZKB_E_INVALID;
   zkb_engine* e = b->eng;

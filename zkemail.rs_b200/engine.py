@@ -142,7 +142,7 @@ EXPORTED_SYMBOLS = (
     "zkb_batch_prepare", "zkb_batch_run", "zkb_batch_run_async", "zkb_batch_fetch",
     "zkb_batch_destroy", "zkb_batch_get_stats", "zkb_batch_last_timing", "zkb_engine_stream",
     "zkb_regex_compile", "zkb_free", "zkb_sha256_batch", "zkb_rsa_verify_batch",
-    "zkb_dfa_scan_batch", "zkb_int_pipe_peaks", "zkb_host_canonicalize",
+    "zkb_dfa_scan_batch", "zkb_int_pipe_peaks", "zkb_host_canonicalize", "zkb_batch_device_flags",
 )
 
 _lib = None
@@ -189,6 +189,7 @@ def load_library():
     L.zkb_batch_destroy.restype = None
     L.zkb_batch_get_stats.argtypes = [vp, C.POINTER(BatchStats)]
     L.zkb_batch_last_timing.argtypes = [vp, C.POINTER(C.c_float * 5)]
+    L.zkb_batch_device_flags.argtypes = [vp, sz, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
     L.zkb_engine_stream.argtypes = [vp]
     L.zkb_engine_stream.restype = vp
     L.zkb_regex_compile.argtypes = [C.c_char_p, sz, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp),
@@ -394,6 +395,17 @@ class PreparedBatch:
         s = BatchStats()
         _check(self.engine.lib.zkb_batch_get_stats(self.handle, C.byref(s)), "zkb_batch_get_stats")
         return s.as_dict()
+
+    def device_flags(self):
+        """[(device pointer, count)] of the per-candidate verdict words of every resident chunk."""
+        nch = C.c_size_t()
+        _check(self.engine.lib.zkb_batch_device_flags(self.handle, 1 << 60, None, None, C.byref(nch)), "zkb_batch_device_flags")
+        out = []
+        for i in range(nch.value):
+            p, n = C.c_void_p(), C.c_size_t()
+            _check(self.engine.lib.zkb_batch_device_flags(self.handle, i, C.byref(p), C.byref(n), None), "zkb_batch_device_flags")
+            out.append((p.value, n.value))
+        return out
 
     def fetch(self) -> np.ndarray:
         out = np.zeros(self.views.n, dtype=RESULT_DTYPE)
