@@ -1,0 +1,175 @@
+"""GPU parity on the edge cases the domain has: empty and ragged batches,
+extreme sizes, every status code, several signatures per message, odd keys.  Everything goes
+through the C ABI; the oracle is the checker."""
+import hashlib
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+import oracle
+import zkemail_rs_b200 as z
+from zkemail_rs_b200 import synth
+from zkemail_rs_b200.structs import RegexInfo, RegexPattern, CompiledRegex
+from tests.util import NOW, assert_records_equal, key_pool
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(engine, emails, labels=None):
+    got = engine.verify_batch(emails)
+    exp = oracle.verify_batch(emails, now=NOW)
+    for i, (g, e) in enumerate(zip(got, exp)):
+        assert_records_equal(g, e, labels[i] if labels else i)
+    return got
+
+
+def test_empty_and_single_batches(engine):
+    assert len(engine.verify_batch([])) == 0
+    rng = np.random.default_rng(1)
+    e = synth.make_email(rng, key_pool()[2048][0], "a.example.com", idx=0, body_len=10)
+    _check(engine, [e])
+    assert engine.sha256_batch([]) == []
+    assert engine.sha256_batch([b""]) == [hashlib.sha256(b"").digest()]
+
+
+def test_ragged_sizes_and_large_body(engine):
+    rng = np.random.default_rng(2)
+    keys = key_pool()
+    sizes = [0, 1, 2, 3, 61, 62, 63, 64, 65, 117, 118, 119, 120, 121, 1023, 1024, 1025, 65536, 300_000, 1_200_000]
+    emails = [synth.make_email(rng, keys[2048 if i % 3 else 1024][i % 2], f"r{i % 4}.example.com", idx=i, body_len=s)
+              for i, s in enumerate(sizes)]
+    got = _check(engine, emails)
+    assert all(int(g["status"]) == 0 for g in got)
+
+
+def test_every_status_code(engine):
+    rng = np.random.default_rng(3)
+    k = key_pool()[2048][0]
+    base = synth.make_email(rng, k, "s.example.com", idx=1, body_len=200)
+    P = z.PublicKey
+    emails = [
+        base,                                                                        # 0 OK
+        z.Email(base.from_domain, b" leading space\r\n\r\nbody", base.public_key),   # 1 MAIL_PARSE
+        z.Email(base.from_domain, b"A: b\r\n\rX", base.public_key),                  # 1 (lone CR after headers)
+        z.Email(base.from_domain, base.raw_email, P(b"\x30\x00", "rsa")),            # 2 KEY
+        z.Email(base.from_domain, base.raw_email, P(k.der, "dsa")),                  # 2
+        z.Email(base.from_domain, base.raw_email, P(k.der[:-1], "rsa")),             # 2 (truncated DER)
+        z.Email(base.from_domain, base.raw_email, P(b"\x01" * 32, "ed25519")),       # 9 UNSUPPORTED
+        z.Email(base.from_domain, base.raw_email, P(b"\x01" * 31, "ed25519")),       # 2
+        synth.make_email(rng, k, "s.example.com", idx=2, body_len=50, algo="rsa-sha1"),        # 9
+        synth.make_email(rng, k, "s.example.com", idx=3, body_len=50, algo="ed25519-sha256"),  # 3 / ALGO_KEY_MISMATCH
+        synth.make_email(rng, k, "s.example.com", idx=4, body_len=50, algo="rsa-md5"),         # 3 / HASH_ALGO
+        synth.make_email(rng, k, "s.example.com", idx=5, body_len=50, canon="relaxed/strict"), # 3 / CANON_TYPE
+        synth.make_email(rng, k, "s.example.com", idx=6, body_len=50, extra_tags=" x=1000;"),  # 3 / EXPIRED
+        synth.make_email(rng, k, "s.example.com", idx=7, body_len=50, extra_tags=" q=dns/other;"),
+        synth.make_email(rng, k, "s.example.com", idx=8, body_len=50, extra_tags=" l=abc;"),
+        synth.make_email(rng, k, "s.example.com", idx=9, body_len=50, extra_tags=" i=@other.org;"),
+        synth.make_email(rng, k, "s.example.com", idx=10, body_len=50, h=("to", "subject")),   # From not signed
+        z.Email(base.from_domain, b"no headers at all", base.public_key),
+        z.Email(base.from_domain, b"", base.public_key),
+        z.Email("", base.raw_email, base.public_key),
+        z.Email(base.from_domain.upper(), base.raw_email, base.public_key),          # domain compare is case-insensitive
+    ]
+    got = _check(engine, emails)
+    st_ = [int(g["status"]) for g in got]
+    assert st_[:9] == [0, 1, 1, 2, 2, 2, 9, 2, 9]
+    assert int(got[9]["dkim_detail"]) == 15 and int(got[10]["dkim_detail"]) == 10 and int(got[11]["dkim_detail"]) == 9
+    assert st_[-1] == 0
+
+
+def test_l_tag_and_truncated_body(engine):
+    rng = np.random.default_rng(4)
+    k = key_pool()[2048][1]
+    # l=100 covers exactly the signed (canonical-stable, CRLF-terminated) body: text appended after
+    # signing must not break the signature; l=99 truncates the hashed body and must
+    headers = synth.default_headers(rng, "l.example.com", 1)
+    body = synth.synth_body(rng, 100)
+    raw = synth.sign_email(headers, body, k, "l.example.com", extra_tags=" l=100;")
+    e1 = z.Email("l.example.com", raw + b"appended after signing\r\n", z.PublicKey(k.der, "rsa"))
+    e2 = z.Email("l.example.com", raw.replace(b" l=100;", b" l=99;"), z.PublicKey(k.der, "rsa"))
+    got = _check(engine, [e1, e2])
+    assert int(got[0]["status"]) == 0 and int(got[1]["status"]) == 3
+
+
+def test_multiple_signatures(engine):
+    rng = np.random.default_rng(5)
+    k0, k1 = key_pool()[2048][0], key_pool()[2048][1]
+    good = synth.make_email(rng, k0, "a.example.com", idx=1, body_len=300)
+    raw = good.raw_email
+    other = synth.make_email(rng, k1, "b.example.com", idx=2, body_len=300).raw_email
+    other_sig = other[: other.find(b"Received:")]
+    broken = raw[: raw.find(b"Received:")].replace(b"bh=", b"bh=A", 1)
+    simple = synth.make_email(rng, k0, "a.example.com", idx=3, body_len=300, canon="simple/simple")
+    emails = [
+        z.Email("a.example.com", other_sig + broken + raw, good.public_key),      # third signature passes
+        z.Email("a.example.com", other_sig + broken + raw[raw.find(b"Received:"):], good.public_key),
+        z.Email("c.example.com", raw, good.public_key),                           # neutral
+        z.Email("a.example.com", broken + broken + broken + raw, good.public_key),
+        simple,
+    ]
+    got = _check(engine, emails)
+    assert [int(g["status"]) for g in got] == [0, 3, 3, 0, 0]
+    # with regex: the haystacks come from the FIRST valid signature (other domain), not the verifying one
+    info = RegexInfo([CompiledRegex(z.compile_regex(r"d=b\.example\.com"), None)], None)
+    g2 = engine.verify_with_regex_batch(emails[:1], info)
+    e2 = oracle.verify_batch(emails[:1], info.header_parts, None, now=NOW)
+    assert_records_equal(g2[0], e2[0], "haystack-from-first-valid-signature")
+    assert int(g2[0]["status"]) == 0
+
+
+def _forge(nbits, e, rng):
+    from tests.test_emu_kernels import _prime, _der
+    import math
+    while True:
+        p, q = _prime(nbits // 2, rng), _prime(nbits - nbits // 2, rng)
+        n, phi = p * q, (p - 1) * (q - 1)
+        if n.bit_length() == nbits and math.gcd(e, phi) == 1:
+            return n, pow(e, -1, phi), _der(n, e)
+
+
+@pytest.mark.parametrize("nbits,e", [(2047, 65537), (1536, 65537), (2048, 3), (1000, 17), (3072, 65537), (4096, 65537), (768, 65537)])
+def test_odd_keys_through_the_rsa_entry_point(engine, nbits, e):
+    rng = np.random.default_rng(nbits + e)
+    n, d, der = _forge(nbits, e, rng)
+    k = (nbits + 7) // 8
+    ks, ds, ss = [], [], []
+    for i in range(8):
+        h = hashlib.sha256(b"m%d" % i).digest()
+        em = b"\x00\x01" + b"\xff" * (k - 54) + b"\x00" + bytes.fromhex("3031300d060960864801650304020105000420") + h
+        s = pow(int.from_bytes(em, "big"), d, n)
+        if i % 4 == 1:
+            s ^= 1 << 9
+        if i % 4 == 2:
+            h = hashlib.sha256(b"other").digest()
+        ks.append(der); ds.append(h); ss.append(s.to_bytes(k, "big"))
+    got = engine.rsa_verify_batch(ks, ds, ss)
+    exp = [oracle.rsa_verify_sha256(a, b, c) for a, b, c in zip(ks, ds, ss)]
+    assert got == exp and sum(got) == 4
+
+
+_NAME = st.sampled_from([b"From", b"from", b"To", b"Subject", b"Date", b"X-Test", b"Cc"])
+_VAL = st.lists(st.sampled_from([b"a", b"B", b" ", b"\t", b"  ", b"\r\n ", b"x@y.z", b";", b"=", b"\xc3\xa9", b"\xff"]), max_size=8).map(b"".join)
+_BODY = st.lists(st.sampled_from([b"line", b" ", b"\t", b"\r\n", b"\n", b"\r", b"=\r\n", b"  ", b"text text", b""]), max_size=14).map(b"".join)
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(st.lists(st.tuples(st.lists(st.tuples(_NAME, _VAL), min_size=1, max_size=6), _BODY,
+                          st.sampled_from(["relaxed/relaxed", "simple/simple", "relaxed/simple", "simple/relaxed"])),
+                min_size=1, max_size=8))
+def test_dirty_mail_batches_vs_oracle(engine, mails):
+    """Randomly dirty (but signed) mail: folds, tabs, bare CR/LF, non-ASCII, odd canonicalisation."""
+    rng = np.random.default_rng(7)
+    k = key_pool()[2048][0]
+    emails = []
+    for headers, body, canon in mails:
+        hs = [(n.decode("latin1"), v.rstrip(b"\r\n\t ").decode("latin1")) for n, v in headers]
+        if not any(n.lower() == "from" for n, _ in hs):
+            hs.append(("From", "x@d.example.com"))
+        try:
+            raw = synth.sign_email(hs, body, k, "d.example.com", canon=canon)
+        except Exception:
+            continue
+        emails.append(z.Email("d.example.com", raw, z.PublicKey(k.der, "rsa")))
+    if emails:
+        _check(engine, emails)

@@ -133,8 +133,18 @@ struct DkimSig {
   size_t n = 0;
   std::string lossy, vals;
   std::vector<Tag> tags;
+  // O(1) lookup of the tag names the verifier asks for: v a b d h s c l i q x (by letter) and bh
+  int16_t known[27];
+  static int slot_of(const uint8_t* name, size_t len) {
+    if (len == 1 && name[0] >= 'a' && name[0] <= 'z') return name[0] - 'a';
+    if (len == 2 && name[0] == 'b' && name[1] == 'h') return 26;
+    return -1;
+  }
+  void reset() { tags.clear(); vals.clear(); for (auto& k : known) k = -1; }
   const Tag* get(const char* name) const {
     size_t l = strlen(name);
+    int k = slot_of((const uint8_t*)name, l);
+    if (k >= 0) return known[k] >= 0 ? &tags[known[k]] : nullptr;
     for (const Tag& t : tags)
       if (t.name_len == l && memcmp(s + t.name_off, name, l) == 0) return &t;
     return nullptr;
@@ -169,8 +179,7 @@ inline const uint8_t* chartab() { static const CharTab T; return T.t; }
 inline int validate_dkim_header(const uint8_t* raw_val, size_t raw_len, int64_t now_unix, DkimSig& sig) {
   using namespace detail;
   const uint8_t* CT = chartab();
-  sig.tags.clear();
-  sig.vals.clear();
+  sig.reset();
   bool ascii = true;
   {
     size_t i = 0;
@@ -219,10 +228,18 @@ inline int validate_dkim_header(const uint8_t* raw_val, size_t raw_len, int64_t 
     t.val_len = (uint32_t)(sig.vals.size() - t.val_off);
     while (p < n && (CT[s[p]] & C_FWS)) p++;
     // IndexMap insert: a later duplicate replaces the value in the first one's position
+    const int slot = DkimSig::slot_of(s + t.name_off, t.name_len);
     bool dup = false;
-    for (Tag& o : sig.tags)
-      if (o.name_len == t.name_len && memcmp(s + o.name_off, s + t.name_off, t.name_len) == 0) { o = t; dup = true; break; }
-    if (!dup) sig.tags.push_back(t);
+    if (slot >= 0) {
+      if (sig.known[slot] >= 0) { sig.tags[sig.known[slot]] = t; dup = true; }
+    } else {
+      for (Tag& o : sig.tags)
+        if (o.name_len == t.name_len && memcmp(s + o.name_off, s + t.name_off, t.name_len) == 0) { o = t; dup = true; break; }
+    }
+    if (!dup) {
+      if (slot >= 0 && sig.tags.size() < 32000) sig.known[slot] = (int16_t)sig.tags.size();
+      sig.tags.push_back(t);
+    }
     pos = p;
     first = false;
   }

@@ -11,6 +11,8 @@
 // There is no CPU fallback for the arithmetic: without a CUDA device zkb_engine_create fails.
 #include <cuda_runtime.h>
 
+#include <stddef.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -45,24 +47,30 @@ namespace {
   } while (0)
 
 // ------------------------------------------------------------------ thread pool
+// Parallel phases follow one another within microseconds in the chunk pipeline, so workers spin on a
+// generation counter for a short while before falling back to a condition variable.
 class ThreadPool {
  public:
   explicit ThreadPool(int n) : n_(n < 1 ? 1 : n) {
     for (int i = 1; i < n_; i++) th_.emplace_back([this, i] { worker(i); });
   }
   ~ThreadPool() {
-    { std::lock_guard<std::mutex> l(mu_); stop_ = true; gen_++; }
+    { std::lock_guard<std::mutex> l(mu_); stop_.store(true); gen_.fetch_add(1); }
     cv_.notify_all();
     for (auto& t : th_) t.join();
   }
   int size() const { return n_; }
   // runs fn(tid) once on every thread of the pool (the caller is tid 0) and waits for all
   void run(const std::function<void(int)>& fn) {
-    { std::lock_guard<std::mutex> l(mu_); job_ = &fn; pending_ = n_ - 1; gen_++; }
-    cv_.notify_all();
+    job_ = &fn;
+    pending_.store(n_ - 1, std::memory_order_release);
+    { std::lock_guard<std::mutex> l(mu_); gen_.fetch_add(1, std::memory_order_release); }
+    if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
     fn(0);
-    std::unique_lock<std::mutex> l(mu_);
-    done_.wait(l, [this] { return pending_ == 0; });
+    int spins = 0;
+    while (pending_.load(std::memory_order_acquire) != 0) {
+      if (++spins < 2000) cpu_relax(); else std::this_thread::yield();
+    }
     job_ = nullptr;
   }
   // dynamic parallel-for over [0,n) in grains
@@ -79,30 +87,37 @@ class ThreadPool {
   }
 
  private:
+  static void cpu_relax() {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
   void worker(int tid) {
     uint64_t seen = 0;
     for (;;) {
-      const std::function<void(int)>* job;
-      {
+      int spins = 0;
+      while (gen_.load(std::memory_order_acquire) == seen) {
+        if (++spins < 20000) { cpu_relax(); continue; }
         std::unique_lock<std::mutex> l(mu_);
-        cv_.wait(l, [&] { return gen_ != seen; });
-        seen = gen_;
-        if (stop_) return;
-        job = job_;
+        sleepers_.fetch_add(1);
+        cv_.wait(l, [&] { return gen_.load(std::memory_order_acquire) != seen; });
+        sleepers_.fetch_sub(1);
       }
+      seen = gen_.load(std::memory_order_acquire);
+      if (stop_.load()) return;
+      const std::function<void(int)>* job = job_;
       if (job) (*job)(tid);
-      { std::lock_guard<std::mutex> l(mu_); pending_--; }
-      done_.notify_one();
+      pending_.fetch_sub(1, std::memory_order_acq_rel);
     }
   }
   int n_;
   std::vector<std::thread> th_;
   std::mutex mu_;
-  std::condition_variable cv_, done_;
-  const std::function<void(int)>* job_ = nullptr;
-  uint64_t gen_ = 0;
-  int pending_ = 0;
-  bool stop_ = false;
+  std::condition_variable cv_;
+  const std::function<void(int)>* volatile job_ = nullptr;
+  std::atomic<uint64_t> gen_{0};
+  std::atomic<int> pending_{0}, sleepers_{0};
+  std::atomic<bool> stop_{false};
 };
 
 // ------------------------------------------------------------------ pinned staging blocks
@@ -187,6 +202,7 @@ struct CandRec {        // one DKIM-Signature header that reaches the cryptograp
   uint32_t sig_off;            // word offset into the thread's signature words
   int32_t key_id;
   uint8_t bh_valid, sig_state, algo, haystack_only;
+  uint8_t rsa_list;            // which of the 6 RSA launch lists (valid when the candidate goes to the device)
 };
 enum { STEP_ERR = 0, STEP_CAND = 1, STEP_SHA1 = 2 };
 struct StepRec { uint32_t cand; uint8_t kind, detail; };
@@ -205,8 +221,15 @@ struct ThreadRecs {
   std::vector<CandRec> cands;
   std::vector<StepRec> steps;
   std::vector<uint32_t> sigw;
+  std::vector<uint32_t> hist;       // messages per SHA block count (maintained by commit)
+  uint64_t sha_blocks = 0, sha_bytes = 0;
+  uint32_t rsa_cnt[6] = {0, 0, 0, 0, 0, 0};
   uint32_t msg_base = 0, cand_base = 0;
-  void clear() { msgs.clear(); cands.clear(); steps.clear(); sigw.clear(); }
+  void clear() {
+    msgs.clear(); cands.clear(); steps.clear(); sigw.clear(); hist.clear();
+    sha_blocks = sha_bytes = 0;
+    for (auto& c : rsa_cnt) c = 0;
+  }
 };
 
 struct DeviceChunk {   // everything one chunk needs in HBM
@@ -287,6 +310,8 @@ struct zkb_batch {
 
 namespace {
 
+inline int rsa_list_of(const KeyMeta& k) { return (k.limbs_class == 32 ? 0 : k.limbs_class == 64 ? 1 : 2) * 2 + (k.generic ? 1 : 0); }
+
 // ------------------------------------------------------------------ per-thread parse context
 struct ThreadCtx {
   zkb_engine* eng;
@@ -322,6 +347,10 @@ struct ThreadCtx {
     MsgRec m;
     m.goff = 0; m.len = (uint32_t)len; m.blk = blk; m.local = local;
     tr->msgs.push_back(m);
+    const uint32_t nb = (uint32_t)(len >> 6) + 1 + ((len & 63) >= 56 ? 1u : 0u);  // SHA-256 compressions
+    if (tr->hist.size() <= nb) tr->hist.resize((size_t)nb + 1, 0u);
+    tr->hist[nb]++;
+    tr->sha_blocks += nb; tr->sha_bytes += len;
     return (uint32_t)tr->msgs.size() - 1;
   }
   uint32_t add_msg(const uint8_t* data, size_t len) {
@@ -436,6 +465,8 @@ void process_email(ThreadCtx& c, const zkb_email_view& em, bool want_regex, int 
       else if ((size_t)sl != km.k) cd.sig_state = SIG_BADLEN;
       else if (algo == 1) {
         cd.sig_state = SIG_OK;
+        cd.rsa_list = (uint8_t)rsa_list_of(km);
+        c.tr->rsa_cnt[cd.rsa_list]++;
         cd.sig_off = (uint32_t)c.tr->sigw.size();
         c.tr->sigw.resize(c.tr->sigw.size() + km.limbs_class, 0u);
         uint32_t* w = c.tr->sigw.data() + cd.sig_off;
@@ -519,7 +550,6 @@ void process_email(ThreadCtx& c, const zkb_email_view& em, bool want_regex, int 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 double g_prof_parse = 0, g_prof_layout = 0;  // ZKB_PROFILE accounting (single caller per engine)
 inline double now_s2() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-inline int rsa_list_of(const KeyMeta& k) { return (k.limbs_class == 32 ? 0 : k.limbs_class == 64 ? 1 : 2) * 2 + (k.generic ? 1 : 0); }
 
 // Host pack of emails [e0, e0+ne): parallel parse + layout of the SoA meta buffers.
 int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne, const zkb_regex_set* rs, Chunk& ch, PinBuf& pin_meta) {
@@ -561,11 +591,23 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
   }
   ch.arena_bytes = (size_t)off + 128;
   ch.M = M; ch.C = C;
-  // RSA lists
+  // RSA lists and message-order buckets from the counters the threads kept while parsing
   uint32_t rn[6] = {0, 0, 0, 0, 0, 0};
-  for (auto& t : ch.tr)
-    for (auto& cd : t.cands)
-      if (!cd.haystack_only && cd.sig_state == SIG_OK && cd.algo == 1) rn[rsa_list_of(e->key_meta[cd.key_id])]++;
+  std::vector<uint32_t> rsa_start((size_t)T * 6, 0);
+  for (int t = 0; t < T; t++)
+    for (int k = 0; k < 6; k++) { rsa_start[(size_t)t * 6 + k] = rn[k]; rn[k] += ch.tr[t].rsa_cnt[k]; }
+  uint32_t maxb = 0;
+  uint64_t sha_blocks = 0, sha_bytes = 0;
+  for (auto& t : ch.tr) { maxb = std::max<uint32_t>(maxb, t.hist.empty() ? 0u : (uint32_t)t.hist.size() - 1); sha_blocks += t.sha_blocks; sha_bytes += t.sha_bytes; }
+  // order: descending block count; inside a bucket by thread, then by message index
+  std::vector<std::vector<uint32_t>> ord_start(T);
+  {
+    for (int t = 0; t < T; t++) ord_start[t].assign(ch.tr[t].hist.size(), 0u);
+    uint32_t acc = 0;
+    for (uint32_t b = maxb + 1; b-- > 0;)
+      for (int t = 0; t < T; t++)
+        if (b < ch.tr[t].hist.size()) { ord_start[t][b] = acc; acc += ch.tr[t].hist[b]; }
+  }
   const size_t P = rs ? rs->n_active() : 0;
   uint32_t n_dfa = 0;
   if (P) for (auto& er : ch.emails) if (er.status == ZKB_ST_OK && er.canon_rc == 0) n_dfa++;
@@ -589,61 +631,36 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
   uint32_t* cand_body = (uint32_t*)(mh + ch.o_cand_body);
   uint32_t* cand_bh = (uint32_t*)(mh + ch.o_cand_bh);
   uint32_t* sigw = (uint32_t*)(mh + ch.o_sig);
-  // per-thread slices (parallel)
   std::vector<size_t> sig_base(T, 0);
-  { size_t s = 0; for (int t = 0; t < T; t++) { sig_base[t] = s; s += ch.tr[t].sigw.size(); } }
-  uint64_t sha_blocks = 0, sha_bytes = 0;
+  { size_t sb = 0; for (int t = 0; t < T; t++) { sig_base[t] = sb; sb += ch.tr[t].sigw.size(); } }
+  // one parallel pass: every thread lays out the records it produced
   e->pool->run([&](int tid) {
     ThreadRecs& t = ch.tr[tid];
+    std::vector<uint32_t>& os = ord_start[tid];
     for (size_t i = 0; i < t.msgs.size(); i++) {
       MsgRec& m = t.msgs[i];
       m.goff = t.blocks[m.blk].dev_off + m.local;
       msg_off[t.msg_base + i] = m.goff;
       msg_len[t.msg_base + i] = m.len;
+      const uint32_t nb = (m.len >> 6) + 1 + ((m.len & 63) >= 56 ? 1u : 0u);
+      order[os[nb]++] = t.msg_base + (uint32_t)i;
     }
+    uint32_t fill[6];
+    for (int k = 0; k < 6; k++) fill[k] = rsa_start[(size_t)tid * 6 + k];
     for (size_t i = 0; i < t.cands.size(); i++) {
       const CandRec& cd = t.cands[i];
       cand_body[t.cand_base + i] = t.msg_base + cd.body_msg;
       memcpy(cand_bh + (size_t)(t.cand_base + i) * 8, cd.bh, 32);
+      if (cd.haystack_only || cd.sig_state != SIG_OK || cd.algo != 1) continue;
+      RsaItem it;
+      it.sig_off = (uint32_t)(sig_base[tid] + cd.sig_off);
+      it.key_id = (uint32_t)cd.key_id;
+      it.digest_slot = t.msg_base + cd.hdr_msg;
+      it.cand = t.cand_base + (uint32_t)i;
+      ((RsaItem*)(mh + ch.o_rsa[cd.rsa_list]))[fill[cd.rsa_list]++] = it;
     }
     if (!t.sigw.empty()) memcpy(sigw + sig_base[tid], t.sigw.data(), t.sigw.size() * 4);
   });
-  // message order: descending block count (counting sort), keeps the lanes of a warp converged
-  {
-    uint32_t maxb = 0;
-    std::vector<uint32_t> nb(M);
-    for (uint32_t i = 0; i < M; i++) {
-      uint32_t len = msg_len[i];
-      uint32_t b = (len >> 6) + 1 + ((len & 63) >= 56 ? 1 : 0);
-      nb[i] = b; maxb = std::max(maxb, b);
-      sha_blocks += b; sha_bytes += len;
-    }
-    std::vector<uint32_t> cnt((size_t)maxb + 2, 0);
-    for (uint32_t i = 0; i < M; i++) cnt[maxb - nb[i]]++;
-    uint32_t acc = 0;
-    for (size_t b = 0; b <= maxb; b++) { uint32_t c = cnt[b]; cnt[b] = acc; acc += c; }
-    for (uint32_t i = 0; i < M; i++) order[cnt[maxb - nb[i]]++] = i;
-  }
-  // RSA items
-  {
-    uint32_t fill[6] = {0, 0, 0, 0, 0, 0};
-    for (int tid = 0; tid < T; tid++) {
-      ThreadRecs& t = ch.tr[tid];
-      for (size_t i = 0; i < t.cands.size(); i++) {
-        const CandRec& cd = t.cands[i];
-        if (cd.haystack_only || cd.sig_state != SIG_OK || cd.algo != 1) continue;
-        const KeyMeta& km = e->key_meta[cd.key_id];
-        int k = rsa_list_of(km);
-        RsaItem* items = (RsaItem*)(mh + ch.o_rsa[k]);
-        RsaItem it;
-        it.sig_off = (uint32_t)(sig_base[tid] + cd.sig_off);
-        it.key_id = (uint32_t)cd.key_id;
-        it.digest_slot = t.msg_base + cd.hdr_msg;
-        it.cand = t.cand_base + (uint32_t)i;
-        items[fill[k]++] = it;
-      }
-    }
-  }
   // DFA items: for each email with haystacks, slot 2*j = header preimage, 2*j+1 = canonical body
   uint64_t dfa_bytes = 0;
   if (P) {
@@ -791,7 +808,7 @@ void cleaned_span(const HayView& h, bool qp, uint32_t start, uint32_t end, std::
 void resolve_email(const zkb_engine* e, const Chunk& ch, size_t i, const uint8_t* outp, size_t o_flags, size_t o_dfa,
                    const zkb_regex_set* rs, const zkb_email_captures* caps, const std::function<HayView(const ThreadRecs&, const MsgRec&)>& hay,
                    zkb_result& res, std::string& s1, std::string& s2) {
-  memset(&res, 0, sizeof res);
+  memset(&res, 0, rs ? sizeof res : offsetof(zkb_result, parts));  // parts[] stay untouched when n_parts = 0
   res.dkim_detail = ZKB_DKIM_NEUTRAL;
   const EmailRec& er = ch.emails[i];
   if (er.status != ZKB_ST_OK) { res.status = er.status; return; }
