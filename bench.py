@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--host-threads", type=int, default=0)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--no-direct", action="store_true", help="pageable inputs: host-side canonicalisation + host copy into pinned staging")
     ap.add_argument("--seed", type=int, default=0xD1C1)
     args = ap.parse_args()
 
@@ -253,6 +254,11 @@ def main():
                    rsa_lanes=args.rsa_lanes)
     views_np = pool.engine_views(order)
     views = EmailViews.from_arrays(views_np, keep=pool)
+    direct = not args.no_direct
+    if direct:  # inputs start in pinned host memory (bench contract): zero-copy DMA + device-side canonicalisation
+        t0 = time.time()
+        eng.register_host(pool.raw)
+        log(f"cudaHostRegister of the raw pool ({pool.raw.nbytes / 1e9:.2f} GB): {time.time() - t0:.2f}s")
     regex = None
     if wl["regex"]:
         info = RegexInfo([CompiledRegex(z.compile_regex(p), None) for p in REGEX_CONFIG["header"]],
@@ -409,6 +415,8 @@ def main():
                        "negatives": "1% (body flip / signature flip / wrong key)", "keys": f"{wl['keys2048']}x2048+{wl['keys1024']}x1024",
                        "l2": f"inputs larger than L2: {stats['arena_bytes'] / 1e9:.2f} GB arena per step",
                        "host_threads": threads, "parallelism": f"shard-by-email x{world}",
+                       "input_memory": "registered (pinned) host memory: raw messages DMA'd as they are, bodies canonicalised on the device" if direct
+                                       else "pageable host memory: bodies canonicalised on host threads into pinned staging",
                        "collective": "none (1 GPU)" if world == 1 else "NCCL all-gather of verdict words per step (inside the timed region)", "rsa_lanes": args.rsa_lanes or 8},
             "roofline": roofline, "roofline_int": roofline_int, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "emails/s", "h2d_bytes_per_step": stats["h2d_bytes"],
@@ -419,6 +427,8 @@ def main():
         print(json.dumps(line), flush=True)
     if regex is not None:
         regex.close()
+    if direct:
+        eng.unregister_host(pool.raw)
     eng.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -122,6 +122,14 @@ const char *zkb_strerror(int code);
 int zkb_engine_create(const zkb_options *opt, zkb_engine **out);
 void zkb_engine_destroy(zkb_engine *e);
 
+/* Optional zero-copy input path.  Registers caller memory holding raw messages with the CUDA driver
+ * (page-locks it; cudaHostRegister).  Batches whose zkb_email_view.raw_email pointers all lie inside
+ * one registered range are DMA'd to the device as they are - no host copy - and their bodies are
+ * canonicalised on the device (canon.cuh) instead of on the host threads.  Results are identical
+ * either way.  Unregister before freeing the memory. */
+int zkb_host_register(zkb_engine *e, const void *p, size_t len);
+int zkb_host_unregister(zkb_engine *e, const void *p);
+
 /* Registers the DFAs of a RegexInfo (core/src/structs.rs:32-35): n_header header parts followed
  * by n_body body parts.  header_present/body_present==0 model `None` (the part list is skipped,
  * core/src/circuits.rs:39-56). Tables are validated (bad bytes => ZKB_E_REGEX, the per-email

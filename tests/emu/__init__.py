@@ -95,3 +95,28 @@ def dfa_scan(fwd, bwd, hays, qp=False, use_smem=True, table_form=0):
                             1 if use_smem else 0, _p(out), table_form)
     assert rc == 0
     return out
+
+
+def canon_bodies(bodies, relaxed=True, l=None):
+    """The device canonicalisation kernel source over bodies placed at odd offsets of a span buffer."""
+    n = len(bodies)
+    off, cur = [], 5
+    for b in bodies:
+        off.append(cur)
+        cur += len(b) + 3   # deliberately unaligned, bodies adjacent to foreign bytes
+    span = np.full(cur + 64, 0x20, dtype=np.uint8)   # SP garbage around the bodies
+    for o, b in zip(off, bodies):
+        span[o:o + len(b)] = np.frombuffer(b, dtype=np.uint8)
+    slot, c2 = [], 0
+    for b in bodies:
+        slot.append(c2)
+        c2 += ((len(b) + 2) // 64 + 1) * 64
+    arena = np.full(c2 + 64, 0xEE, dtype=np.uint8)
+    offa = np.array(off, dtype=np.uint64)
+    lena = np.array([len(b) for b in bodies], dtype=np.uint32)
+    flags = np.full(n, (1 if relaxed else 0) | (2 if l is not None else 0), dtype=np.uint32)
+    lval = np.full(n, l if l is not None else 0, dtype=np.uint32)
+    slota = np.array(slot, dtype=np.uint64)
+    out_len = np.zeros(n, dtype=np.uint32)
+    lib().emu_canon_body(_p(span), _p(offa), _p(lena), _p(flags), _p(lval), n, _p(arena), _p(slota), _p(out_len))
+    return [arena[s:s + int(k)].tobytes() for s, k in zip(slot, out_len)]

@@ -9,6 +9,7 @@
 #include "../../zkemail.rs_b200/csrc/keytab.hpp"
 #include "../../zkemail.rs_b200/csrc/sha256.cuh"
 #include "../../zkemail.rs_b200/csrc/rsa.cuh"
+#include "../../zkemail.rs_b200/csrc/canon.cuh"
 // dfa.cuh added below once rewritten
 
 using namespace zkb;
@@ -99,10 +100,10 @@ int emu_dfa_scan(const uint8_t* fwd, size_t fl, const uint8_t* bwd, size_t bl, c
     elem = e1;
   }
   std::vector<DfaItem> items(n);
-  for (uint32_t i = 0; i < n; i++) { items[i].hay_off = off[i]; items[i].hay_len = len[i]; items[i].out_slot = i; }
+  for (uint32_t i = 0; i < n; i++) { items[i].hay_off = off[i]; items[i].msg = i; items[i].out_slot = i; }
   const unsigned block = 128;
   emu::launch((n + block - 1) / block, block, [&]() {
-#define RUN1(TT, D, S) dfa_scan_kernel<TT, D, S>(arena, items.data(), n, fb.data(), (uint32_t)fb.size(), rb.data(), (uint32_t)rb.size(), qp, (uint4*)out)
+#define RUN1(TT, D, S) dfa_scan_kernel<TT, D, S>(arena, items.data(), n, len, fb.data(), (uint32_t)fb.size(), rb.data(), (uint32_t)rb.size(), qp, (uint4*)out)
 #define RUN(TT, D) do { if (use_smem) RUN1(TT, D, true); else RUN1(TT, D, false); } while (0)
     if (elem == 2) { if (direct) RUN(uint16_t, true); else RUN(uint16_t, false); }
     else { if (direct) RUN(uint32_t, true); else RUN(uint32_t, false); }
@@ -110,6 +111,18 @@ int emu_dfa_scan(const uint8_t* fwd, size_t fl, const uint8_t* bwd, size_t bl, c
 #undef RUN
   });
   return 0;
+}
+
+// device-side body canonicalisation: n bodies at span[off[i] .. off[i]+len[i]); out slots of cap[i] bytes
+// (64-byte aligned) are packed into `arena`; out_len[i] receives the canonical lengths
+void emu_canon_body(const uint8_t* span, const uint64_t* off, const uint32_t* len, const uint32_t* flags, const uint32_t* lval,
+                    uint32_t n, uint8_t* arena, const uint64_t* slot_off, uint32_t* out_len) {
+  std::vector<CanonItem> items(n);
+  for (uint32_t i = 0; i < n; i++) {
+    items[i].raw_off = off[i]; items[i].raw_len = len[i]; items[i].msg = i; items[i].flags = flags[i]; items[i].l = lval[i];
+  }
+  const unsigned block = 128;
+  emu::launch((n + block - 1) / block, block, [&]() { canon_body_kernel(span, items.data(), n, arena, slot_off, out_len); });
 }
 
 }  // extern "C"

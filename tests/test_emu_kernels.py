@@ -203,3 +203,25 @@ def test_regex_unicode_classes_utf8():
 def test_regex_compiler_rejects(bad):
     with pytest.raises(ValueError):
         emu.regex_compile(bad)
+
+
+_PIECES = [b"line", b" ", b"\t", b"\r\n", b"\n", b"\r", b"=\r\n", b"  ", b"text text", b"", b" \r\n", b"\r\n\r\n", b"x" * 17, b"\t \t"]
+
+
+def test_canon_body_kernel_source_vs_oracle():
+    """Device-side body canonicalisation (canon.cuh) against the oracle on dirty bodies: tabs, WSP
+    runs, SP before CRLF, bare CR/LF, trailing blank lines, missing final CRLF, empty, l= cuts."""
+    rng = np.random.default_rng(5)
+    bodies = [b"", b"\r\n", b"abc ", b" ", b"\t", b"a \r\n", b" \r\r\n", b"a\r\n\r\n\r\n", b"a \t \r\nb", b"\r", b"\n",
+              b" C \r\nD \t E\r\n\r\n\r\n", b"x" * 64, b"y" * 63 + b" ", b"no final newline", b"\r\n\r\n", b" \r\n \r\n"]
+    for _ in range(400):
+        k = int(rng.integers(0, 14))
+        bodies.append(b"".join(_PIECES[i] for i in rng.integers(0, len(_PIECES), size=k)))
+    for relaxed in (True, False):
+        got = emu.canon_bodies(bodies, relaxed=relaxed)
+        for b, g in zip(bodies, got):
+            assert g == oracle.canon_body(b, relaxed), (relaxed, b, g, oracle.canon_body(b, relaxed))
+        for l in (0, 1, 5, 100000):
+            got = emu.canon_bodies(bodies[:60], relaxed=relaxed, l=l)
+            for b, g in zip(bodies[:60], got):
+                assert g == oracle.canon_body(b, relaxed)[:l], (relaxed, l, b, g)

@@ -154,3 +154,57 @@ def test_resident_batch_matches_pipeline(engine):
     pb.close()
     assert a.tobytes() == b.tobytes()
     assert st["n_emails"] == len(emails) and st["kernel_launches"] >= 3
+
+
+def test_direct_mode_device_canonicalisation(engine):
+    """Zero-copy path: raw messages in registered host memory, bodies canonicalised by canon.cuh on the
+    device.  Must equal the oracle AND the host-canonicalisation path record for record."""
+    import os
+    from tests.util import contiguous_views
+    emails, labels = mixed_emails(seed=31, with_token=True)
+    rng = np.random.default_rng(32)
+    k = key_pool()[2048][0]
+    dirty = [b"Trailing space \r\nTab\there  \r\n\r\n\r\n", b"no final newline", b"", b"\r\n", b" \r\n \r\n", b"a\tb  c \r\n\r\n",
+             b"bare\nlf and\rcr\r\n", b"x" * 1000 + b" \r\n" + b"y" * 70 + b"\r\n\r\n\r\n\r\n", b"abc "]
+    for i, body in enumerate(dirty):
+        for canon in ("relaxed/relaxed", "simple/simple"):
+            raw = synth.sign_email(synth.default_headers(rng, "mail0.example.com", 200 + i), body, k, "mail0.example.com", canon=canon)
+            emails.append(z.Email("mail0.example.com", raw, z.PublicKey(k.der, "rsa")))
+            labels.append("pos")
+    buf, views = contiguous_views(emails)
+    exp = oracle.verify_batch(emails, now=NOW)
+    engine.register_host(buf)
+    try:
+        got = engine.verify_views(views)
+        pb = engine.prepare(views)
+        pb.run()
+        got_res = pb.fetch()
+        st = pb.stats()
+        pb.close()
+        os.environ["ZKB_NO_DIRECT"] = "1"
+        host = engine.verify_views(views)
+        del os.environ["ZKB_NO_DIRECT"]
+    finally:
+        os.environ.pop("ZKB_NO_DIRECT", None)
+        engine.unregister_host(buf)
+    for g, e, lab in zip(got, exp, labels):
+        assert_records_equal(g, e, lab)
+    assert got.tobytes() == host.tobytes() == got_res.tobytes()
+    assert sum(int(g["status"]) == 0 for g in got) == labels.count("pos")
+    # with regex + captures: the haystack is the device-canonicalised body; captures are checked on the host
+    hdr, body = oracle.canonicalize_signed_email(emails[0].raw_email, NOW)
+    clean, _ = oracle.qp_clean(body)
+    body_parts = z.compile_regex_parts([RegexPattern(r"Transaction ID: ([A-Z0-9]+)", [1])], clean)
+    info = RegexInfo(None, body_parts)
+    from zkemail_rs_b200.engine import RegexSet
+    rs = RegexSet(engine, info)
+    engine.register_host(buf)
+    try:
+        got2 = engine.verify_views(views, rs)
+    finally:
+        engine.unregister_host(buf)
+        rs.close()
+    exp2 = oracle.verify_batch(emails, None, body_parts, now=NOW)
+    for g, e, lab in zip(got2, exp2, labels):
+        assert_records_equal(g, e, lab)
+    assert int(got2[0]["status"]) == 0

@@ -82,3 +82,27 @@ def assert_records_equal(got, exp, label=""):
     # start/end are only defined when there is at least one match
     norm = lambda ps: [(c, s, e, k) if c else (c, 0, 0, k) for (c, s, e, k) in ps]
     assert norm(parts) == norm(eparts), (label, "parts", parts, eparts)
+
+
+def contiguous_views(emails):
+    """Copies the raw messages of `emails` into ONE numpy buffer (so that it can be registered with the
+    engine for the zero-copy / device-canonicalisation path) and returns (buffer, EmailViews)."""
+    from zkemail_rs_b200.engine import EmailViews
+    import ctypes as C
+    offs, cur = [], 7
+    for e in emails:
+        offs.append(cur)
+        cur += len(e.raw_email) + 13          # odd gaps: bodies start at arbitrary alignments
+    buf = np.full(cur + 64, 0x20, dtype=np.uint8)
+    keep = [buf]
+    v = np.zeros((len(emails), 8), dtype=np.uint64)
+    for i, e in enumerate(emails):
+        raw = np.frombuffer(e.raw_email, dtype=np.uint8)
+        buf[offs[i]:offs[i] + len(raw)] = raw
+        dom = e.from_domain.encode()
+        key = bytes(e.public_key.key)
+        kt = e.public_key.key_type.encode()
+        keep += [dom, key, kt]
+        v[i] = [C.cast(C.c_char_p(dom), C.c_void_p).value or 0, len(dom), buf.ctypes.data + offs[i], len(raw),
+                C.cast(C.c_char_p(key), C.c_void_p).value or 0, len(key), C.cast(C.c_char_p(kt), C.c_void_p).value or 0, len(kt)]
+    return buf, EmailViews.from_arrays(v, keep)

@@ -36,11 +36,22 @@ struct __align__(16) RsaItem {
   uint32_t sig_off, key_id, digest_slot, cand;
 };
 
-// One DFA scan item. hay_off in bytes into the arena.
+// One DFA scan item: haystack = arena[hay_off .. hay_off + msg_len[msg]) (the length lives in the
+// device-side message table because device-canonicalised bodies only get theirs on the device).
 struct __align__(16) DfaItem {
   uint64_t hay_off;
-  uint32_t hay_len;
+  uint32_t msg;
   uint32_t out_slot;
+};
+
+// One body to canonicalise on the device (canon.cuh).
+struct __align__(16) CanonItem {
+  uint64_t raw_off;   // body bytes in the raw span buffer
+  uint32_t raw_len;
+  uint32_t msg;       // message index: arena slot msg_off[msg], length written to msg_len[msg]
+  uint32_t flags;     // bit0 relaxed, bit1 has l=
+  uint32_t l;         // l= value (clamped to 2^32-1)
+  uint32_t pad[2];
 };
 
 // Per-candidate flags written by the device

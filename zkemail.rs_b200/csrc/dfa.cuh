@@ -279,8 +279,8 @@ __device__ __forceinline__ uint4 dfa_scan_one(const uint8_t* fb, const uint8_t* 
 template <typename TT, bool DIRECT, bool SMEM>
 __global__ void __launch_bounds__(128)
 dfa_scan_kernel(const uint8_t* __restrict__ arena, const DfaItem* __restrict__ items,
-                uint32_t n_items, const uint8_t* __restrict__ fwd_blob, uint32_t fwd_bytes,
-                const uint8_t* __restrict__ rev_blob, uint32_t rev_bytes, int qp,
+                uint32_t n_items, const uint32_t* __restrict__ msg_len, const uint8_t* __restrict__ fwd_blob,
+                uint32_t fwd_bytes, const uint8_t* __restrict__ rev_blob, uint32_t rev_bytes, int qp,
                 uint4* __restrict__ out) {
   ZKB_DYN_SMEM(smem);
   const uint8_t *fb, *rb;
@@ -288,7 +288,7 @@ dfa_scan_kernel(const uint8_t* __restrict__ arena, const DfaItem* __restrict__ i
   uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_items) return;
   DfaItem it = items[idx];
-  out[it.out_slot] = dfa_scan_one<TT, DIRECT>(fb, rb, arena + it.hay_off, it.hay_len, qp);
+  out[it.out_slot] = dfa_scan_one<TT, DIRECT>(fb, rb, arena + it.hay_off, msg_len[it.msg], qp);
 }
 
 // Engine form: items are interleaved per email (2*j = header preimage, 2*j+1 = canonical body);
@@ -296,7 +296,8 @@ dfa_scan_kernel(const uint8_t* __restrict__ arena, const DfaItem* __restrict__ i
 template <typename TT, bool DIRECT, bool SMEM>
 __global__ void __launch_bounds__(128)
 dfa_scan_strided(const uint8_t* __restrict__ arena, const DfaItem* __restrict__ items, uint32_t n_emails,
-                 uint32_t which, uint32_t P, uint32_t pi, const uint8_t* __restrict__ fwd_blob, uint32_t fwd_bytes,
+                 const uint32_t* __restrict__ msg_len, uint32_t which, uint32_t P, uint32_t pi,
+                 const uint8_t* __restrict__ fwd_blob, uint32_t fwd_bytes,
                  const uint8_t* __restrict__ rev_blob, uint32_t rev_bytes, int qp,
                  uint4* __restrict__ out) {
   ZKB_DYN_SMEM(smem);
@@ -305,7 +306,7 @@ dfa_scan_strided(const uint8_t* __restrict__ arena, const DfaItem* __restrict__ 
   uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_emails) return;
   DfaItem it = items[2 * idx + which];
-  out[(size_t)it.out_slot * P + pi] = dfa_scan_one<TT, DIRECT>(fb, rb, arena + it.hay_off, it.hay_len, qp);
+  out[(size_t)it.out_slot * P + pi] = dfa_scan_one<TT, DIRECT>(fb, rb, arena + it.hay_off, msg_len[it.msg], qp);
 }
 
 }  // namespace zkb

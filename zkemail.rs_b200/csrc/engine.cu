@@ -193,8 +193,11 @@ struct DevBuf {  // growable device buffer
 // ------------------------------------------------------------------ records produced by the host pass
 struct MsgRec {         // one SHA-256 message / DFA haystack
   uint64_t goff;        // byte offset in the device arena (after layout)
-  uint32_t len, blk, local;
+  uint32_t len, blk, local;  // blk == VIRT_BLK: a body canonicalised on the device; local = offset in the
+                             // thread's virtual region, len = raw length (upper-bound estimate), canon = its item
+  uint32_t canon;
 };
+constexpr uint32_t VIRT_BLK = 0xFFFFFFFFu;
 enum { SIG_OK = 0, SIG_SYNTAX = 1, SIG_BADLEN = 2 };
 struct CandRec {        // one DKIM-Signature header that reaches the cryptographic checks
   uint32_t body_msg, hdr_msg;  // thread-local message indices
@@ -221,19 +224,25 @@ struct ThreadRecs {
   std::vector<CandRec> cands;
   std::vector<StepRec> steps;
   std::vector<uint32_t> sigw;
+  std::vector<CanonItem> canon;     // bodies to canonicalise on the device (direct mode)
+  uint64_t virt_used = 0, virt_base = 0;   // device-only arena region of this thread (canonical body slots)
+  uint32_t canon_base = 0;
   std::vector<uint32_t> hist;       // messages per SHA block count (maintained by commit)
   uint64_t sha_blocks = 0, sha_bytes = 0;
   uint32_t rsa_cnt[6] = {0, 0, 0, 0, 0, 0};
   uint32_t msg_base = 0, cand_base = 0;
   void clear() {
-    msgs.clear(); cands.clear(); steps.clear(); sigw.clear(); hist.clear();
+    msgs.clear(); cands.clear(); steps.clear(); sigw.clear(); hist.clear(); canon.clear();
+    virt_used = 0;
     sha_blocks = sha_bytes = 0;
     for (auto& c : rsa_cnt) c = 0;
   }
 };
 
 struct DeviceChunk {   // everything one chunk needs in HBM
-  DevBuf arena, meta, out;
+  DevBuf arena, meta, out, span;   // span: raw message bytes DMA'd from registered host memory (direct mode)
+  const CanonItem* canon_items = nullptr; uint32_t n_canon = 0;
+  uint32_t* msg_len_rw = nullptr;
   // pointers into meta / out
   const uint64_t* msg_off = nullptr; const uint32_t* msg_len = nullptr; const uint32_t* order = nullptr;
   const uint32_t* cand_body = nullptr; const uint32_t* cand_bh = nullptr;
@@ -243,7 +252,7 @@ struct DeviceChunk {   // everything one chunk needs in HBM
   uint32_t* digests = nullptr; uint32_t* cand_flags = nullptr; uint4* dfa_out = nullptr;
   uint32_t M = 0, C = 0, NE = 0, P = 0;
   size_t out_bytes = 0;
-  void free() { arena.free(); meta.free(); out.free(); }
+  void free() { arena.free(); meta.free(); out.free(); span.free(); }
 };
 
 struct Chunk {  // host view of one chunk
@@ -256,6 +265,11 @@ struct Chunk {  // host view of one chunk
   // offsets inside meta
   size_t o_msg_off = 0, o_msg_len = 0, o_order = 0, o_cand_body = 0, o_cand_bh = 0, o_sig = 0, o_rsa[6] = {0}, o_dfa = 0;
   uint32_t rsa_n[6] = {0}, n_dfa = 0;
+  // direct mode: raw bodies stay in the caller's registered memory and are canonicalised on the device
+  bool direct = false;
+  const uint8_t* span_host = nullptr;
+  size_t span_bytes = 0, o_canon = 0;
+  uint32_t n_canon = 0;
 };
 
 struct Slot {
@@ -286,6 +300,7 @@ struct zkb_engine {
   BlockPool blocks;
   Slot slots[3];
   std::mutex run_mu;
+  std::vector<std::pair<const uint8_t*, size_t>> registered;  // cudaHostRegister'ed caller memory
   // public keys
   std::mutex key_mu;
   std::unordered_map<std::string, int32_t> key_index;
@@ -327,6 +342,30 @@ struct ThreadCtx {
   std::unordered_map<int32_t, uint32_t> key_msgs;
   std::string last_dom; uint32_t last_dom_msg = 0; bool have_last_dom = false;
   bool oom = false;
+  bool direct = false;                 // bodies are canonicalised on the device from the raw span
+  const uint8_t* span_host = nullptr;
+
+  // a device-only arena slot for a body the canon kernel will write (no host bytes)
+  uint32_t add_virtual_body(const uint8_t* body, size_t body_len, bool relaxed, bool has_l, uint64_t l) {
+    CanonItem it;
+    memset(&it, 0, sizeof it);
+    it.raw_off = (uint64_t)(body - span_host);
+    it.raw_len = (uint32_t)body_len;
+    it.flags = (relaxed ? 1u : 0u) | (has_l ? 2u : 0u);
+    it.l = l > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)l;
+    it.msg = (uint32_t)tr->msgs.size();   // thread-local; made global at layout
+    MsgRec m;
+    m.goff = 0; m.len = (uint32_t)body_len + 2; m.blk = VIRT_BLK; m.local = (uint32_t)tr->virt_used;
+    m.canon = (uint32_t)tr->canon.size();
+    tr->virt_used += (((body_len + 2) >> 6) + 1) << 6;
+    tr->canon.push_back(it);
+    tr->msgs.push_back(m);
+    const uint32_t nb = (uint32_t)(m.len >> 6) + 1 + ((m.len & 63) >= 56 ? 1u : 0u);  // estimate from the raw length
+    if (tr->hist.size() <= nb) tr->hist.resize((size_t)nb + 1, 0u);
+    tr->hist[nb]++;
+    tr->sha_blocks += nb; tr->sha_bytes += body_len;
+    return (uint32_t)tr->msgs.size() - 1;
+  }
 
   // reserve `need` bytes (64-byte aligned start) in the thread's current staging block
   uint8_t* reserve(size_t need, uint32_t& blk, uint32_t& local) {
@@ -345,7 +384,7 @@ struct ThreadCtx {
     PinBlock& b = tr->blocks[blk];
     b.used = local + (((len >> 6) + 1) << 6);  // readable up to the block after the last full one
     MsgRec m;
-    m.goff = 0; m.len = (uint32_t)len; m.blk = blk; m.local = local;
+    m.goff = 0; m.len = (uint32_t)len; m.blk = blk; m.local = local; m.canon = 0;
     tr->msgs.push_back(m);
     const uint32_t nb = (uint32_t)(len >> 6) + 1 + ((len & 63) >= 56 ? 1u : 0u);  // SHA-256 compressions
     if (tr->hist.size() <= nb) tr->hist.resize((size_t)nb + 1, 0u);
@@ -429,12 +468,17 @@ void process_email(ThreadCtx& c, const zkb_email_view& em, bool want_regex, int 
     for (int i = 0; i < n_bodies; i++)
       if (bodies[i].relaxed == relaxed && bodies[i].has_l == has_l && bodies[i].l == l) return bodies[i].msg;
     if (!body_found) { body = find_body(raw, n, body_len, body_off); body_found = true; }
-    uint32_t blk, local;
-    uint8_t* p = c.reserve((((body_len + 2) >> 6) + 1) << 6, blk, local);
-    if (!p) return 0;
-    size_t cl = relaxed ? canon_body_relaxed(body, body_len, p) : canon_body_simple(body, body_len, p);
-    if (has_l && l < cl) cl = (size_t)l;
-    uint32_t m = c.commit(blk, local, cl);
+    uint32_t m;
+    if (c.direct) {
+      m = c.add_virtual_body(body, body_len, relaxed, has_l, l);
+    } else {
+      uint32_t blk, local;
+      uint8_t* p = c.reserve((((body_len + 2) >> 6) + 1) << 6, blk, local);
+      if (!p) return 0;
+      size_t cl = relaxed ? canon_body_relaxed(body, body_len, p) : canon_body_simple(body, body_len, p);
+      if (has_l && l < cl) cl = (size_t)l;
+      m = c.commit(blk, local, cl);
+    }
     if (n_bodies < 4) { bodies[n_bodies].relaxed = relaxed; bodies[n_bodies].has_l = has_l; bodies[n_bodies].l = l; bodies[n_bodies].msg = m; n_bodies++; }
     return m;
   };
@@ -562,10 +606,33 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
   std::atomic<size_t> next{0};
   std::atomic<int> oom{0};
   const double tp0 = now_s2();
+  // direct mode: every message of the chunk lies in one registered host range and the chunk's span is
+  // not much larger than its payload -> one DMA of the raw span, bodies canonicalised on the device
+  ch.direct = false; ch.span_host = nullptr; ch.span_bytes = 0; ch.n_canon = 0;
+  if (ne && !e->registered.empty() && !getenv("ZKB_NO_DIRECT")) {
+    const uint8_t* lo = emails[e0].raw_email;
+    const uint8_t* hi = lo;
+    size_t payload = 0;
+    for (size_t i = 0; i < ne; i++) {
+      const zkb_email_view& v = emails[e0 + i];
+      lo = std::min(lo, v.raw_email); hi = std::max(hi, v.raw_email + v.raw_email_len);
+      payload += v.raw_email_len;
+    }
+    for (auto& r : e->registered) {
+      if (lo >= r.first && hi <= r.first + r.second && (size_t)(hi - lo) <= payload + payload / 2 + (1u << 20) &&
+          (size_t)(hi - lo) < ((size_t)3 << 30)) {
+        const uint8_t* base = (const uint8_t*)((uintptr_t)lo & ~(uintptr_t)255);
+        if (base < r.first) base = r.first;
+        ch.direct = true; ch.span_host = base; ch.span_bytes = (size_t)(hi - base);
+        break;
+      }
+    }
+  }
   const size_t grain = std::max<size_t>(16, std::min<size_t>(512, ne / (size_t)(T * 8) + 1));
   e->pool->run([&](int tid) {
     ThreadCtx c;
     c.eng = e; c.tr = &ch.tr[tid];
+    c.direct = ch.direct; c.span_host = ch.span_host;
     for (;;) {
       size_t lo = next.fetch_add(grain);
       if (lo >= ne) break;
@@ -581,14 +648,17 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
   g_prof_parse += tp1 - tp0;
   // layout: device arena = concatenation of the used parts of all staging blocks
   uint64_t off = 0;
-  uint32_t M = 0, C = 0;
+  uint32_t M = 0, C = 0, NC = 0;
   size_t sig_words = 0;
   for (auto& t : ch.tr) {
     for (auto& b : t.blocks) { b.dev_off = off; off += align_up(b.used, 128); }
-    t.msg_base = M; t.cand_base = C;
-    M += (uint32_t)t.msgs.size(); C += (uint32_t)t.cands.size();
+    t.msg_base = M; t.cand_base = C; t.canon_base = NC;
+    M += (uint32_t)t.msgs.size(); C += (uint32_t)t.cands.size(); NC += (uint32_t)t.canon.size();
     sig_words += t.sigw.size();
   }
+  const uint64_t staged_bytes = off;   // what travels host -> device out of the staging blocks
+  for (auto& t : ch.tr) { t.virt_base = off; off += align_up(t.virt_used, 128); }  // device-only canonical body slots
+  ch.n_canon = NC;
   ch.arena_bytes = (size_t)off + 128;
   ch.M = M; ch.C = C;
   // RSA lists and message-order buckets from the counters the threads kept while parsing
@@ -622,6 +692,7 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
   ch.o_sig = o; o += align_up(sig_words * 4, 16);
   for (int k = 0; k < 6; k++) { ch.o_rsa[k] = o; ch.rsa_n[k] = rn[k]; o += align_up((size_t)rn[k] * sizeof(RsaItem), 16); }
   ch.o_dfa = o; o += align_up((size_t)n_dfa * 2 * sizeof(DfaItem), 16);  // header haystack + body haystack per email
+  ch.o_canon = o; o += align_up((size_t)NC * sizeof(CanonItem), 16);
   ch.meta_bytes = o + 16;
   if (!pin_meta.ensure(ch.meta_bytes)) return ZKB_E_NOMEM;
   uint8_t* mh = pin_meta.p;  // every array below is written in full; padding bytes are never read
@@ -639,7 +710,7 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
     std::vector<uint32_t>& os = ord_start[tid];
     for (size_t i = 0; i < t.msgs.size(); i++) {
       MsgRec& m = t.msgs[i];
-      m.goff = t.blocks[m.blk].dev_off + m.local;
+      m.goff = m.blk == VIRT_BLK ? t.virt_base + m.local : t.blocks[m.blk].dev_off + m.local;
       msg_off[t.msg_base + i] = m.goff;
       msg_len[t.msg_base + i] = m.len;
       const uint32_t nb = (m.len >> 6) + 1 + ((m.len & 63) >= 56 ? 1u : 0u);
@@ -660,6 +731,8 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
       ((RsaItem*)(mh + ch.o_rsa[cd.rsa_list]))[fill[cd.rsa_list]++] = it;
     }
     if (!t.sigw.empty()) memcpy(sigw + sig_base[tid], t.sigw.data(), t.sigw.size() * 4);
+    CanonItem* ci = (CanonItem*)(mh + ch.o_canon) + t.canon_base;
+    for (size_t i = 0; i < t.canon.size(); i++) { ci[i] = t.canon[i]; ci[i].msg += t.msg_base; }
   });
   // DFA items: for each email with haystacks, slot 2*j = header preimage, 2*j+1 = canonical body
   uint64_t dfa_bytes = 0;
@@ -673,8 +746,8 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
       const CandRec& cd = t.cands[er.canon_cand];
       const MsgRec& hm = t.msgs[cd.hdr_msg];
       const MsgRec& bm = t.msgs[cd.body_msg];
-      items[2 * j].hay_off = hm.goff; items[2 * j].hay_len = hm.len; items[2 * j].out_slot = (uint32_t)i;
-      items[2 * j + 1].hay_off = bm.goff; items[2 * j + 1].hay_len = bm.len; items[2 * j + 1].out_slot = (uint32_t)i;
+      items[2 * j].hay_off = hm.goff; items[2 * j].msg = t.msg_base + cd.hdr_msg; items[2 * j].out_slot = (uint32_t)i;
+      items[2 * j + 1].hay_off = bm.goff; items[2 * j + 1].msg = t.msg_base + cd.body_msg; items[2 * j + 1].out_slot = (uint32_t)i;
       dfa_bytes += (uint64_t)hm.len * (rs->header_present ? rs->n_header : 0) + (uint64_t)bm.len * (rs->body_present ? rs->n_body : 0);
       j++;
     }
@@ -690,7 +763,7 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
   }
   ch.st.dfa_items = (uint64_t)n_dfa * P; ch.st.dfa_bytes = dfa_bytes;
   ch.st.arena_bytes = ch.arena_bytes;
-  ch.st.h2d_bytes = off + ch.meta_bytes;
+  ch.st.h2d_bytes = staged_bytes + ch.meta_bytes + (ch.direct ? ch.span_bytes : 0);
   g_prof_layout += now_s2() - tp1;
   return ZKB_OK;
 }
@@ -713,6 +786,14 @@ int upload_chunk(zkb_engine* e, Chunk& ch, const zkb_regex_set* rs, DeviceChunk&
     for (auto& b : t.blocks)
       if (b.used) CK(cudaMemcpyAsync(d.arena.p + b.dev_off, b.p, b.used, cudaMemcpyHostToDevice, stream));
   CK(cudaMemcpyAsync(d.meta.p, pin_meta.p, ch.meta_bytes, cudaMemcpyHostToDevice, stream));
+  d.n_canon = 0;
+  if (ch.direct && ch.n_canon) {
+    if (!d.span.ensure(ch.span_bytes + 256)) return ZKB_E_NOMEM;
+    CK(cudaMemcpyAsync(d.span.p, ch.span_host, ch.span_bytes, cudaMemcpyHostToDevice, stream));  // DMA from registered memory
+    d.canon_items = (const CanonItem*)(d.meta.p + ch.o_canon);
+    d.n_canon = ch.n_canon;
+  }
+  d.msg_len_rw = (uint32_t*)(d.meta.p + ch.o_msg_len);
   CK(cudaMemsetAsync(d.out.p + o_flags, 0, align_up((size_t)ch.C * 4, 16), stream));
   if (P) CK(cudaMemsetAsync(d.out.p + o_dfa, 0, ch.ne * P * 16, stream));
   d.msg_off = (const uint64_t*)(d.meta.p + ch.o_msg_off);
@@ -754,6 +835,7 @@ int sync_keytab(zkb_engine* e, cudaStream_t stream) {
 // Enqueues every kernel of one chunk.  ev (optional): 5 events recorded around the kernel families.
 int launch_chunk(zkb_engine* e, const DeviceChunk& d, const zkb_regex_set* rs, cudaStream_t s, cudaEvent_t* ev, uint64_t* launches) {
   uint64_t nl = 0;
+  if (d.n_canon) { launch_canon_body(d.span.p, d.canon_items, d.n_canon, d.arena.p, d.msg_off, d.msg_len_rw, s); nl++; }
   if (ev) CK(cudaEventRecord(ev[0], s));
   if (d.M) { launch_sha256(d.arena.p, d.msg_off, d.msg_len, d.order, d.M, d.digests, s); nl++; }
   if (ev) CK(cudaEventRecord(ev[1], s));
@@ -777,7 +859,7 @@ int launch_chunk(zkb_engine* e, const DeviceChunk& d, const zkb_regex_set* rs, c
       const zkb_regex_set::Part& part = rs->parts[p];
       if (part.body ? !rs->body_present : !rs->header_present) continue;
       // items are interleaved (header, body) per email; out slot = email * P + pi
-      launch_dfa_strided(part.elem, part.direct, d.arena.p, d.dfa_items, d.n_dfa, part.body ? 1u : 0u, (uint32_t)d.P, (uint32_t)pi, part.d_fwd,
+      launch_dfa_strided(part.elem, part.direct, d.arena.p, d.dfa_items, d.n_dfa, d.msg_len, part.body ? 1u : 0u, (uint32_t)d.P, (uint32_t)pi, part.d_fwd,
                          part.fwd_bytes, part.d_rev, part.rev_bytes, e->smem_optin, part.body ? 1 : 0, d.dfa_out, s);
       nl++; pi++;
     }
@@ -805,8 +887,22 @@ void cleaned_span(const HayView& h, bool qp, uint32_t start, uint32_t end, std::
   }
 }
 
+// Host bytes of a haystack for the capture check.  Bodies canonicalised on the device (direct mode) are
+// re-canonicalised here on demand from the caller's raw bytes: only emails with captures to check pay.
+HayView hay_view(const Chunk& ch, const ThreadRecs& t, const MsgRec& m, std::vector<uint8_t>& scratch) {
+  HayView v;
+  if (m.blk != VIRT_BLK) { v.p = t.blocks[m.blk].p + m.local; v.n = m.len; return v; }
+  const CanonItem& it = t.canon[m.canon];
+  const uint8_t* raw = ch.span_host + it.raw_off;
+  scratch.resize((size_t)it.raw_len + 64);
+  size_t cl = (it.flags & 1u) ? canon_body_relaxed(raw, it.raw_len, scratch.data()) : canon_body_simple(raw, it.raw_len, scratch.data());
+  if ((it.flags & 2u) && it.l < cl) cl = it.l;
+  v.p = scratch.data(); v.n = (uint32_t)cl;
+  return v;
+}
+
 void resolve_email(const zkb_engine* e, const Chunk& ch, size_t i, const uint8_t* outp, size_t o_flags, size_t o_dfa,
-                   const zkb_regex_set* rs, const zkb_email_captures* caps, const std::function<HayView(const ThreadRecs&, const MsgRec&)>& hay,
+                   const zkb_regex_set* rs, const zkb_email_captures* caps, std::vector<uint8_t>& scratch,
                    zkb_result& res, std::string& s1, std::string& s2) {
   memset(&res, 0, rs ? sizeof res : offsetof(zkb_result, parts));  // parts[] stay untouched when n_parts = 0
   res.dkim_detail = ZKB_DKIM_NEUTRAL;
@@ -867,7 +963,7 @@ void resolve_email(const zkb_engine* e, const Chunk& ch, size_t i, const uint8_t
       for (size_t q = 0; q < ec.n_caps && ok; q++) {
         if (ec.caps[q].part != p) continue;
         if (!loaded) {
-          HayView hv = hay(t, t.msgs[body ? cc.body_msg : cc.hdr_msg]);
+          HayView hv = hay_view(ch, t, t.msgs[body ? cc.body_msg : cc.hdr_msg], scratch);
           cleaned_span(hv, body, r.y, r.z, s1);
           bool ascii = true;
           for (char ch2 : s1) if (ch2 & 0x80) { ascii = false; break; }
@@ -883,13 +979,14 @@ void resolve_email(const zkb_engine* e, const Chunk& ch, size_t i, const uint8_t
 }
 
 void resolve_chunk(zkb_engine* e, const Chunk& ch, const uint8_t* outp, const zkb_regex_set* rs, const zkb_email_captures* caps,
-                   const std::function<HayView(const ThreadRecs&, const MsgRec&)>& hay, zkb_result* out) {
+                   zkb_result* out) {
   const size_t P = rs ? rs->n_active() : 0;
   size_t o_flags, o_dfa;
   out_layout(ch.M, ch.C, ch.ne, P, o_flags, o_dfa);
   e->pool->parallel_for(ch.ne, 256, [&](size_t lo, size_t hi, int) {
     std::string s1, s2;
-    for (size_t i = lo; i < hi; i++) resolve_email(e, ch, i, outp, o_flags, o_dfa, rs, caps, hay, out[ch.e0 + i], s1, s2);
+    std::vector<uint8_t> scratch;
+    for (size_t i = lo; i < hi; i++) resolve_email(e, ch, i, outp, o_flags, o_dfa, rs, caps, scratch, out[ch.e0 + i], s1, s2);
   });
 }
 
@@ -969,9 +1066,33 @@ void zkb_engine_destroy(zkb_engine* e) {
   }
   for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
   if (e->d_keytab) cudaFree(e->d_keytab);
+  for (auto& r : e->registered) cudaHostUnregister(const_cast<uint8_t*>(r.first));
   e->blocks.release_all();
   delete e->pool;
   delete e;
+}
+
+int zkb_host_register(zkb_engine* e, const void* p, size_t len) {
+  if (!e || !p || !len) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lock(e->run_mu);
+  CK(cudaSetDevice(e->device));
+  CK(cudaHostRegister(const_cast<void*>(p), len, cudaHostRegisterPortable));
+  e->registered.emplace_back((const uint8_t*)p, len);
+  return ZKB_OK;
+}
+
+int zkb_host_unregister(zkb_engine* e, const void* p) {
+  if (!e || !p) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lock(e->run_mu);
+  CK(cudaSetDevice(e->device));
+  for (size_t i = 0; i < e->registered.size(); i++)
+    if (e->registered[i].first == (const uint8_t*)p) {
+      CK(cudaDeviceSynchronize());
+      CK(cudaHostUnregister(const_cast<void*>(p)));
+      e->registered.erase(e->registered.begin() + (long)i);
+      return ZKB_OK;
+    }
+  return ZKB_E_INVALID;
 }
 
 void* zkb_engine_stream(zkb_engine* e) { return e ? (void*)e->slots[0].stream : nullptr; }
@@ -1057,8 +1178,7 @@ int zkb_verify_batch(zkb_engine* e, const zkb_email_view* emails, size_t n, cons
     CK(cudaEventSynchronize(s.done));
     double tb = now_s();
     t_wait += tb - ta;
-    auto hay = [&](const ThreadRecs& t, const MsgRec& m) { HayView v; v.p = t.blocks[m.blk].p + m.local; v.n = m.len; return v; };
-    resolve_chunk(e, ch, s.result.p, regex, captures, hay, out);
+    resolve_chunk(e, ch, s.result.p, regex, captures, out);
     release_blocks(e, ch);
     busy[si] = false;
     t_resolve += now_s() - tb;
@@ -1245,8 +1365,7 @@ int zkb_batch_fetch(zkb_batch* b, zkb_result* out) {
     if (!res.ensure(d.out_bytes)) return ZKB_E_NOMEM;
     CK(cudaMemcpyAsync(res.p, d.out.p, d.out_bytes, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    auto hay = [&](const ThreadRecs& t, const MsgRec& m) { HayView v; v.p = t.blocks[m.blk].p + m.local; v.n = m.len; return v; };
-    resolve_chunk(e, ch, res.p, b->regex, b->captures, hay, out);
+    resolve_chunk(e, ch, res.p, b->regex, b->captures, out);
   }
   return ZKB_OK;
 }
@@ -1410,20 +1529,22 @@ int zkb_dfa_scan_batch(zkb_engine* e, const zkb_dfa_view* part, const uint8_t* d
   std::vector<DfaItem> items(n);
   for (size_t i = 0; i < n; i++) {
     if (off[i] + len[i] > data_len) { zkb_regex_set_destroy(rs); return ZKB_E_INVALID; }
-    items[i].hay_off = off[i]; items[i].hay_len = len[i]; items[i].out_slot = (uint32_t)i;
+    items[i].hay_off = off[i]; items[i].msg = (uint32_t)i; items[i].out_slot = (uint32_t)i;
   }
-  uint8_t* d_arena; DfaItem* d_items; uint4* d_out;
+  uint8_t* d_arena; DfaItem* d_items; uint4* d_out; uint32_t* d_hlen;
   CK(cudaMalloc((void**)&d_arena, data_len + 64)); CK(cudaMalloc((void**)&d_items, n * sizeof(DfaItem))); CK(cudaMalloc((void**)&d_out, n * 16));
+  CK(cudaMalloc((void**)&d_hlen, n * 4));
+  CK(cudaMemcpy(d_hlen, len, n * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_arena, data, data_len, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_items, items.data(), n * sizeof(DfaItem), cudaMemcpyHostToDevice));
   CK(cudaMemset(d_out, 0, n * 16));
   const zkb_regex_set::Part& p = rs->parts[0];
   cudaStream_t s = e->slots[0].stream;
-  launch_dfa(p.elem, p.direct, d_arena, d_items, (uint32_t)n, p.d_fwd, p.fwd_bytes, p.d_rev, p.rev_bytes, e->smem_optin, qp, d_out, s);
+  launch_dfa(p.elem, p.direct, d_arena, d_items, (uint32_t)n, d_hlen, p.d_fwd, p.fwd_bytes, p.d_rev, p.rev_bytes, e->smem_optin, qp, d_out, s);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s));
   CK(cudaMemcpy(out, d_out, n * 16, cudaMemcpyDeviceToHost));
-  cudaFree(d_arena); cudaFree(d_items); cudaFree(d_out);
+  cudaFree(d_arena); cudaFree(d_items); cudaFree(d_out); cudaFree(d_hlen);
   zkb_regex_set_destroy(rs);
   return ZKB_OK;
 }

@@ -27,22 +27,22 @@ cudaError_t dfa_set_smem_limit(size_t bytes) {
 #undef ZKB_SET
   return cudaSuccess;
 }
-void launch_dfa(uint32_t elem, bool direct, const uint8_t* arena, const DfaItem* items, uint32_t n_items, const uint8_t* fwd_blob,
+void launch_dfa(uint32_t elem, bool direct, const uint8_t* arena, const DfaItem* items, uint32_t n_items, const uint32_t* msg_len, const uint8_t* fwd_blob,
                 uint32_t fwd_bytes, const uint8_t* rev_blob, uint32_t rev_bytes, size_t smem_limit, int qp, uint4* out,
                 cudaStream_t s) {
   if (!n_items) return;
   size_t smem = (size_t)fwd_bytes + rev_bytes;
   const bool use_smem = smem <= smem_limit;
   unsigned grid = (n_items + 127) / 128;
-  ZKB_DFA_DISPATCH(dfa_scan_kernel, arena, items, n_items, fwd_blob, fwd_bytes, rev_blob, rev_bytes, qp, out);
+  ZKB_DFA_DISPATCH(dfa_scan_kernel, arena, items, n_items, msg_len, fwd_blob, fwd_bytes, rev_blob, rev_bytes, qp, out);
 }
-void launch_dfa_strided(uint32_t elem, bool direct, const uint8_t* arena, const DfaItem* items, uint32_t n_emails, uint32_t which,
+void launch_dfa_strided(uint32_t elem, bool direct, const uint8_t* arena, const DfaItem* items, uint32_t n_emails, const uint32_t* msg_len, uint32_t which,
                         uint32_t P, uint32_t pi, const uint8_t* fwd_blob, uint32_t fwd_bytes, const uint8_t* rev_blob,
                         uint32_t rev_bytes, size_t smem_limit, int qp, uint4* out, cudaStream_t s) {
   if (!n_emails) return;
   size_t smem = (size_t)fwd_bytes + rev_bytes;
   const bool use_smem = smem <= smem_limit;
   unsigned grid = (n_emails + 127) / 128;
-  ZKB_DFA_DISPATCH(dfa_scan_strided, arena, items, n_emails, which, P, pi, fwd_blob, fwd_bytes, rev_blob, rev_bytes, qp, out);
+  ZKB_DFA_DISPATCH(dfa_scan_strided, arena, items, n_emails, msg_len, which, P, pi, fwd_blob, fwd_bytes, rev_blob, rev_bytes, qp, out);
 }
 }  // namespace zkb

@@ -22,12 +22,14 @@ void launch_rsa64(bool generic, int lanes, const uint32_t* sig_arena, const RsaI
 void launch_rsa128(bool generic, int lanes, const uint32_t* sig_arena, const RsaItem* items, uint32_t n,
                    const uint32_t* keytab, const uint32_t* digests, uint32_t* cand_flags, cudaStream_t s);
 cudaError_t dfa_set_smem_limit(size_t bytes);
-void launch_dfa(uint32_t elem, bool direct, const uint8_t* arena, const DfaItem* items, uint32_t n_items, const uint8_t* fwd_blob,
+void launch_dfa(uint32_t elem, bool direct, const uint8_t* arena, const DfaItem* items, uint32_t n_items, const uint32_t* msg_len, const uint8_t* fwd_blob,
                 uint32_t fwd_bytes, const uint8_t* rev_blob, uint32_t rev_bytes, size_t smem_limit, int qp, uint4* out,
                 cudaStream_t s);
-void launch_dfa_strided(uint32_t elem, bool direct, const uint8_t* arena, const DfaItem* items, uint32_t n_emails, uint32_t which,
+void launch_dfa_strided(uint32_t elem, bool direct, const uint8_t* arena, const DfaItem* items, uint32_t n_emails, const uint32_t* msg_len, uint32_t which,
                         uint32_t P, uint32_t pi, const uint8_t* fwd_blob, uint32_t fwd_bytes, const uint8_t* rev_blob,
                         uint32_t rev_bytes, size_t smem_limit, int qp, uint4* out, cudaStream_t s);
+void launch_canon_body(const uint8_t* span, const CanonItem* items, uint32_t n, uint8_t* arena, const uint64_t* msg_off,
+                       uint32_t* msg_len, cudaStream_t s);
 void launch_int_peak(int kind, unsigned grid, unsigned block, uint32_t* out, uint32_t seed, int iters, cudaStream_t s);
 
 }  // namespace zkb

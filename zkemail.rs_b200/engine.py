@@ -143,6 +143,7 @@ EXPORTED_SYMBOLS = (
     "zkb_batch_destroy", "zkb_batch_get_stats", "zkb_batch_last_timing", "zkb_engine_stream",
     "zkb_regex_compile", "zkb_free", "zkb_sha256_batch", "zkb_rsa_verify_batch",
     "zkb_dfa_scan_batch", "zkb_int_pipe_peaks", "zkb_host_canonicalize", "zkb_batch_device_flags",
+    "zkb_host_register", "zkb_host_unregister",
 )
 
 _lib = None
@@ -190,6 +191,8 @@ def load_library():
     L.zkb_batch_get_stats.argtypes = [vp, C.POINTER(BatchStats)]
     L.zkb_batch_last_timing.argtypes = [vp, C.POINTER(C.c_float * 5)]
     L.zkb_batch_device_flags.argtypes = [vp, sz, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
+    L.zkb_host_register.argtypes = [vp, vp, sz]
+    L.zkb_host_unregister.argtypes = [vp, vp]
     L.zkb_engine_stream.argtypes = [vp]
     L.zkb_engine_stream.restype = vp
     L.zkb_regex_compile.argtypes = [C.c_char_p, sz, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp),
@@ -444,6 +447,13 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def register_host(self, array: np.ndarray):
+        """Page-locks caller memory holding raw messages (zero-copy input path, zkb_host_register)."""
+        _check(self.lib.zkb_host_register(self.handle, array.ctypes.data, array.nbytes), "zkb_host_register")
+
+    def unregister_host(self, array: np.ndarray):
+        _check(self.lib.zkb_host_unregister(self.handle, array.ctypes.data), "zkb_host_unregister")
 
     # ---- batch entry points -------------------------------------------------------------
     def verify_views(self, views: EmailViews, regex: Optional[RegexSet] = None, with_captures: bool = True) -> np.ndarray:
