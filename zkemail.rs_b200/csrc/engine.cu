@@ -1263,7 +1263,14 @@ int zkb_batch_prepare(zkb_engine* e, const zkb_email_view* emails, size_t n, con
     if (rc) break;
     rc = upload_chunk(e, *ch, regex, *d, e->slots[0].meta, s);
     if (rc) break;
+    if (d->n_canon) {
+      // resident form: device-side canonicalisation is part of getting the batch resident (it is what
+      // the host threads do on the pageable path); zkb_batch_run then launches the verification kernels
+      launch_canon_body(d->span.p, d->canon_items, d->n_canon, d->arena.p, d->msg_off, d->msg_len_rw, s);
+      d->n_canon = 0;
+    }
     if (cudaStreamSynchronize(s) != cudaSuccess) { rc = ZKB_E_CUDA; break; }
+    d->span.free();
   }
   if (rc) { zkb_batch_destroy(b); return rc; }
   *out = b;
