@@ -10,6 +10,8 @@
 #include "../../zkemail.rs_b200/csrc/sha256.cuh"
 #include "../../zkemail.rs_b200/csrc/rsa.cuh"
 #include "../../zkemail.rs_b200/csrc/canon.cuh"
+#include "../../zkemail.rs_b200/csrc/dkim_host.hpp"
+#include "../../zkemail.rs_b200/csrc/frontend.cuh"
 // dfa.cuh added below once rewritten
 
 using namespace zkb;
@@ -123,6 +125,63 @@ void emu_canon_body(const uint8_t* span, const uint64_t* off, const uint32_t* le
   }
   const unsigned block = 128;
   emu::launch((n + block - 1) / block, block, [&]() { canon_body_kernel(span, items.data(), n, arena, slot_off, out_len); });
+}
+
+// Device front end (frontend.cuh: fe_process) against the host front end (dkim_host.hpp) on one message.
+// returns 0 = the device path declines (fallback), 1 = live and identical to the host, 2 = both report a
+// mail parse error, negative = MISMATCH (code tells which field).
+int emu_fe_compare(const uint8_t* raw, uint32_t n, const uint8_t* dom, uint32_t dom_len, uint32_t k, uint32_t limbs) {
+  std::vector<uint8_t> pre(FE_PRE_CAP + 64, 0xEE);
+  std::vector<uint32_t> sigw(limbs, 0xDEADBEEFu);
+  FeOut fo;
+  fe_process(raw, n, dom, dom_len, k, limbs, pre.data(), sigw.data(), fo);
+  std::vector<HeaderField> hs;
+  size_t body_off = 0;
+  const bool parsed = parse_headers(raw, n, hs, body_off);
+  if (fo.flags & FE_MAIL_PARSE) return parsed ? -1 : 2;
+  if (!parsed) return -2;
+  if (fo.flags & FE_FALLBACK) return 0;
+  // live on the device: the host must reach the cryptographic checks with the same bytes
+  DkimSig sig;
+  std::string scratch;
+  int n_sig = 0, idx = -1;
+  for (size_t i = 0; i < hs.size(); i++)
+    if (ieq_ascii(raw + hs[i].key_off, hs[i].key_len, "DKIM-Signature", 14)) { n_sig++; idx = (int)i; }
+  if (n_sig != 1) return -3;
+  if (validate_dkim_header(raw + hs[idx].val_off, hs[idx].val_len, 1, sig) != ZKB_DKIM_PASS) return -4;
+  const Tag* td = sig.get("d");
+  if (!ieq_ascii(sig.val(td), td->val_len, (const char*)dom, dom_len)) return -5;
+  bool hr, br;
+  if (!parse_canon_tag(sig, hr, br)) return -6;
+  if (!sig.val_is(sig.get("a"), "rsa-sha256")) return -7;
+  if (sig.get("l") || sig.get("x") || sig.get("q") || sig.get("i")) return -8;
+  if (hr != ((fo.flags & FE_HDR_RELAXED) != 0) || br != ((fo.flags & FE_BODY_RELAXED) != 0)) return -9;
+  size_t bl = 0;
+  const uint8_t* b = find_body(raw, n, bl, body_off);
+  if ((size_t)(b - raw) != fo.body_off || bl != fo.body_len) return -10;
+  std::vector<uint8_t> hp(preimage_bound(body_off, sig.n));
+  size_t pl = build_header_preimage(raw, hs, sig, hr, hp.data(), scratch);
+  if (pl != fo.pre_len || memcmp(hp.data(), pre.data(), pl) != 0) return -11;
+  const Tag* tbh = sig.get("bh");
+  uint8_t bh[48];
+  bool bh_valid = tbh->val_len == 44 && base64_decode(sig.val(tbh), 44, bh) == 32;
+  if (bh_valid != ((fo.flags & FE_BH_VALID) != 0)) return -12;
+  if (bh_valid)
+    for (int i = 0; i < 8; i++)
+      if (fo.bh[i] != (((uint32_t)bh[4 * i] << 24) | ((uint32_t)bh[4 * i + 1] << 16) | ((uint32_t)bh[4 * i + 2] << 8) | bh[4 * i + 3])) return -13;
+  const Tag* tb = sig.get("b");
+  std::vector<uint8_t> tmp(tb->val_len + 4);
+  long sl = base64_decode(sig.val(tb), tb->val_len, tmp.data());
+  if ((sl < 0) != ((fo.flags & FE_SIG_SYNTAX) != 0)) return -14;
+  if (sl >= 0 && (((size_t)sl != k) != ((fo.flags & FE_SIG_BADLEN) != 0))) return -15;
+  if (sl >= 0 && (size_t)sl == k) {
+    std::vector<uint32_t> w(limbs, 0);
+    for (long i = 0; i < sl; i++) { long bi = sl - 1 - i; w[bi >> 2] |= (uint32_t)tmp[i] << (8 * (bi & 3)); }
+    if (w != sigw) return -16;
+  } else {
+    for (uint32_t x : sigw) if (x != 0) return -17;
+  }
+  return 1;
 }
 
 }  // extern "C"

@@ -225,3 +225,58 @@ def test_canon_body_kernel_source_vs_oracle():
             got = emu.canon_bodies(bodies[:60], relaxed=relaxed, l=l)
             for b, g in zip(bodies[:60], got):
                 assert g == oracle.canon_body(b, relaxed)[:l], (relaxed, l, b, g)
+
+
+def _fe_compare(raw: bytes, dom: bytes, k=256, limbs=64) -> int:
+    return emu.lib().emu_fe_compare(raw, len(raw), dom, len(dom), k, limbs)
+
+
+def test_device_front_end_source_on_synthetic_mail():
+    """frontend.cuh (device-side header split / tag list / header selection / preimage / base64) against
+    the host front end: live results must be byte-identical; well-formed mail must not fall back."""
+    from tests.util import mixed_emails
+    for seed, tok in ((21, False), (22, True)):
+        emails, labels = mixed_emails(seed=seed, with_token=tok)
+        for e, lab in zip(emails, labels):
+            big = len(e.public_key.key) > 200
+            r = _fe_compare(e.raw_email, e.from_domain.encode(), 256 if big else 128, 64 if big else 32)
+            assert r >= 0, (lab, r)
+            if lab in ("pos", "body_flip", "sig_flip", "wrong_key", "bh_flip", "header_flip"):
+                assert r == 1, (lab, r)
+            if lab in ("domain_mismatch", "missing_tag"):
+                assert r == 0, (lab, r)
+
+
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_FE_NAME = st.sampled_from([b"From", b"from", b"FROM", b"To", b"Subject", b"Date", b"Message-ID", b"X-Test", b"Cc", b"Received", b"Subject "])
+_FE_VAL = st.lists(st.sampled_from([b"a", b"B", b" ", b"\t", b"  ", b"\r\n ", b"\r\n\t", b"x@y.z", b";", b"=", b"\xc3\xa9", b"\r", b"\n "]), max_size=8).map(b"".join)
+_FE_SEP = st.sampled_from([b":", b": ", b":  ", b":\t", b" :"])
+_FE_BODY = st.lists(st.sampled_from([b"line", b" ", b"\r\n", b"\n", b"=\r\n", b"text"]), max_size=6).map(b"".join)
+_FE_B = st.sampled_from([b"QUJD\r\n\t REVG", b"QUJDREVG", b"QUJDRA==", b"QUJ", b"QU JD", b"", b"=QUJD", b"QUJD;", b"QUJD; z=1", b"QUJD ;\r\n"])
+
+
+@settings(max_examples=400, deadline=None)
+@given(st.lists(st.tuples(_FE_NAME, _FE_SEP, _FE_VAL), min_size=1, max_size=7), _FE_BODY,
+       st.sampled_from(["relaxed/relaxed", "simple/simple", "relaxed/simple", "simple/relaxed", "relaxed", "simple", "bogus", None]),
+       st.lists(st.sampled_from(["from", "to", "subject", "date", "cc", "x-test", "From", "message-id", "missing", "subject "]), min_size=0, max_size=6),
+       st.sampled_from(["", " l=5;", " i=@example.com;", " x=99999999999;", " q=dns/txt;", " z=1;", " v=2;", " d=other.org;", " a=rsa-sha1;"]),
+       _FE_B, st.sampled_from(["top", "bottom", "both"]),
+       st.sampled_from([b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA=", b"AAAA", b"AAAAAAAAAAAAAAAAAAAAAA\r\n\tAAAAAAAAAAAAAAAAAAAAA="]))
+def test_device_front_end_source_on_dirty_mail(headers, body, canon, hnames, extra, bval, where, bh):
+    """Whatever the device front end accepts must equal the host front end byte for byte; anything it
+    does not accept must be flagged for the host (never a silent difference)."""
+    block = b"".join(k + s + v.rstrip(b"\r\n\t ") + b"\r\n" if not v.endswith((b"\r\n ", b"\r\n\t", b"\n ")) else k + s + v + b"x\r\n"
+                     for k, s, v in headers)
+    h = ":".join(["from"] + hnames)
+    ctag = f" c={canon};" if canon else ""
+    sig = (f"DKIM-Signature: v=1; a=rsa-sha256;{ctag} d=example.com; s=s;\r\n\th={h};{extra}\r\n\tbh=").encode() + bh + b";\r\n\tb=" + bval + b"\r\n"
+    if where == "top":
+        raw = sig + block
+    elif where == "bottom":
+        raw = block + sig
+    else:
+        raw = sig + block + sig
+    raw += b"\r\n" + body
+    r = _fe_compare(raw, b"Example.COM", k=6, limbs=32)
+    assert r >= 0, (r, raw)

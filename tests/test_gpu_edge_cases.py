@@ -173,3 +173,70 @@ def test_dirty_mail_batches_vs_oracle(engine, mails):
         emails.append(z.Email("d.example.com", raw, z.PublicKey(k.der, "rsa")))
     if emails:
         _check(engine, emails)
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(st.lists(st.tuples(st.lists(st.tuples(_NAME, _VAL), min_size=1, max_size=6), _BODY,
+                          st.sampled_from(["relaxed/relaxed", "simple/simple", "relaxed/simple", "simple/relaxed"])),
+                min_size=1, max_size=8))
+def test_dirty_mail_batches_registered_memory_vs_oracle(engine, mails):
+    """The same dirty mail through the device front end (registered memory)."""
+    from tests.util import contiguous_views
+    k = key_pool()[2048][0]
+    emails = []
+    for headers, body, canon in mails:
+        hs = [(n.decode("latin1"), v.rstrip(b"\r\n\t ").decode("latin1")) for n, v in headers]
+        if not any(n.lower() == "from" for n, _ in hs):
+            hs.append(("From", "x@d.example.com"))
+        try:
+            raw = synth.sign_email(hs, body, k, "d.example.com", canon=canon)
+        except Exception:
+            continue
+        emails.append(z.Email("d.example.com", raw, z.PublicKey(k.der, "rsa")))
+    if not emails:
+        return
+    buf, views = contiguous_views(emails)
+    engine.register_host(buf)
+    try:
+        got = engine.verify_views(views)
+    finally:
+        engine.unregister_host(buf)
+    exp = oracle.verify_batch(emails, now=NOW)
+    for i, (g, e) in enumerate(zip(got, exp)):
+        assert_records_equal(g, e, i)
+
+
+def test_status_codes_registered_memory(engine):
+    """Every status code again, with the messages in registered memory (device front end + fallback)."""
+    from tests.util import contiguous_views
+    rng = np.random.default_rng(3)
+    k = key_pool()[2048][0]
+    base = synth.make_email(rng, k, "s.example.com", idx=1, body_len=200)
+    P = z.PublicKey
+    emails = [
+        base,
+        z.Email(base.from_domain, b" leading space\r\n\r\nbody", base.public_key),
+        z.Email(base.from_domain, b"A: b\r\n\rX", base.public_key),
+        z.Email(base.from_domain, base.raw_email, P(b"\x30\x00", "rsa")),
+        z.Email(base.from_domain, base.raw_email, P(b"\x01" * 32, "ed25519")),
+        synth.make_email(rng, k, "s.example.com", idx=2, body_len=50, algo="rsa-sha1"),
+        synth.make_email(rng, k, "s.example.com", idx=3, body_len=50, algo="ed25519-sha256"),
+        synth.make_email(rng, k, "s.example.com", idx=5, body_len=50, canon="relaxed/strict"),
+        synth.make_email(rng, k, "s.example.com", idx=6, body_len=50, extra_tags=" x=1000;"),
+        synth.make_email(rng, k, "s.example.com", idx=8, body_len=50, extra_tags=" l=abc;"),
+        synth.make_email(rng, k, "s.example.com", idx=10, body_len=50, h=("to", "subject")),
+        z.Email(base.from_domain, b"no headers at all", base.public_key),
+        z.Email(base.from_domain, b"", base.public_key),
+        z.Email(base.from_domain.upper(), base.raw_email, base.public_key),
+        synth.mutate(base, "body_flip", rng), synth.mutate(base, "sig_flip", rng), synth.mutate(base, "bh_flip", rng),
+    ]
+    buf, views = contiguous_views(emails)
+    engine.register_host(buf)
+    try:
+        got = engine.verify_views(views)
+    finally:
+        engine.unregister_host(buf)
+    exp = oracle.verify_batch(emails, now=NOW)
+    for i, (g, e) in enumerate(zip(got, exp)):
+        assert_records_equal(g, e, i)
+    assert [int(g["status"]) for g in got][:5] == [0, 1, 1, 2, 9]

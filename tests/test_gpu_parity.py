@@ -157,8 +157,9 @@ def test_resident_batch_matches_pipeline(engine):
 
 
 def test_direct_mode_device_canonicalisation(engine):
-    """Zero-copy path: raw messages in registered host memory, bodies canonicalised by canon.cuh on the
-    device.  Must equal the oracle AND the host-canonicalisation path record for record."""
+    """Zero-copy path: raw messages in registered host memory; headers parsed / preimages built / base64
+    decoded by frontend.cuh and bodies canonicalised by canon.cuh on the device (irregular messages fall
+    back to the host front end).  Must equal the oracle AND the two host-side paths record for record."""
     import os
     from tests.util import contiguous_views
     emails, labels = mixed_emails(seed=31, with_token=True)
@@ -181,12 +182,17 @@ def test_direct_mode_device_canonicalisation(engine):
         got_res = pb.fetch()
         st = pb.stats()
         pb.close()
-        os.environ["ZKB_NO_DIRECT"] = "1"
+        os.environ["ZKB_NO_DEVICE_FRONTEND"] = "1"      # registered memory, host front end + device canonicalisation
+        mid = engine.verify_views(views)
+        del os.environ["ZKB_NO_DEVICE_FRONTEND"]
+        os.environ["ZKB_NO_DIRECT"] = "1"               # everything on the host threads
         host = engine.verify_views(views)
         del os.environ["ZKB_NO_DIRECT"]
     finally:
         os.environ.pop("ZKB_NO_DIRECT", None)
+        os.environ.pop("ZKB_NO_DEVICE_FRONTEND", None)
         engine.unregister_host(buf)
+    assert got.tobytes() == mid.tobytes()
     for g, e, lab in zip(got, exp, labels):
         assert_records_equal(g, e, lab)
     assert got.tobytes() == host.tobytes() == got_res.tobytes()

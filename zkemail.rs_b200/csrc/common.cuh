@@ -54,6 +54,33 @@ struct __align__(16) CanonItem {
   uint32_t pad[2];
 };
 
+// ---- device front end (frontend.cuh) records ----
+#define FE_MAXH 64      // headers per message handled on the device
+#define FE_MAXN 16      // names in h=
+#define FE_PRE_CAP 4096 // bytes reserved per header preimage slot
+
+enum { FE_FALLBACK = 1u, FE_MAIL_PARSE = 2u, FE_BH_VALID = 4u, FE_SIG_SYNTAX = 8u, FE_SIG_BADLEN = 16u,
+       FE_HDR_RELAXED = 32u, FE_BODY_RELAXED = 64u };
+
+struct __align__(16) FeIn {   // host-built, one per message
+  uint64_t raw_off;           // message bytes in the raw span buffer
+  uint32_t raw_len;
+  uint32_t dom_off;           // from_domain bytes in the arena (staged once per distinct domain)
+  uint32_t dom_len;
+  uint32_t k;                 // byte length of the key's modulus
+  uint32_t limbs;             // limb class of the key (32 / 64 / 128)
+  uint32_t sig_word_off;      // where this message's signature limbs go (words)
+  uint32_t body_msg, pre_msg; // message-table indices of the canonical body / header preimage slots
+  uint32_t cand;              // signature-candidate index (bh= words go to cand_bh[8*cand..])
+  uint32_t pad;
+};
+struct __align__(16) FeOut {
+  uint32_t flags;
+  uint32_t body_off, body_len;   // raw body inside the message (for host-side capture checks)
+  uint32_t pre_len;
+  uint32_t bh[8];
+};
+
 // Per-candidate flags written by the device
 #define ZKB_F_RSA_OK 1u
 #define ZKB_F_BH_OK 2u

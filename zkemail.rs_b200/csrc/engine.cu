@@ -211,6 +211,7 @@ enum { STEP_ERR = 0, STEP_CAND = 1, STEP_SHA1 = 2 };
 struct StepRec { uint32_t cand; uint8_t kind, detail; };
 struct EmailRec {
   int32_t status = 0;
+  uint32_t fe_cand = 0;     // device-front-end mode: thread-local candidate / slot index of this email
   uint32_t tid = 0, first_step = 0, n_steps = 0;
   uint32_t dom_msg = 0, key_msg = 0;
   int32_t canon_rc = 2;     // zo_canonicalize_signed_email return code equivalent
@@ -225,6 +226,7 @@ struct ThreadRecs {
   std::vector<StepRec> steps;
   std::vector<uint32_t> sigw;
   std::vector<CanonItem> canon;     // bodies to canonicalise on the device (direct mode)
+  std::vector<uint32_t> fe_emails;  // device-front-end mode: chunk-local email index of candidate j
   uint64_t virt_used = 0, virt_base = 0;   // device-only arena region of this thread (canonical body slots)
   uint32_t canon_base = 0;
   std::vector<uint32_t> hist;       // messages per SHA block count (maintained by commit)
@@ -232,7 +234,7 @@ struct ThreadRecs {
   uint32_t rsa_cnt[6] = {0, 0, 0, 0, 0, 0};
   uint32_t msg_base = 0, cand_base = 0;
   void clear() {
-    msgs.clear(); cands.clear(); steps.clear(); sigw.clear(); hist.clear(); canon.clear();
+    msgs.clear(); cands.clear(); steps.clear(); sigw.clear(); hist.clear(); canon.clear(); fe_emails.clear();
     virt_used = 0;
     sha_blocks = sha_bytes = 0;
     for (auto& c : rsa_cnt) c = 0;
@@ -243,6 +245,8 @@ struct DeviceChunk {   // everything one chunk needs in HBM
   DevBuf arena, meta, out, span;   // span: raw message bytes DMA'd from registered host memory (direct mode)
   const CanonItem* canon_items = nullptr; uint32_t n_canon = 0;
   uint32_t* msg_len_rw = nullptr;
+  const FeIn* fe_in = nullptr; FeOut* fe_out = nullptr; uint32_t n_fe = 0;   // device front end
+  CanonItem* canon_rw = nullptr; uint32_t* cand_bh_rw = nullptr; uint32_t* sig_rw = nullptr;
   // pointers into meta / out
   const uint64_t* msg_off = nullptr; const uint32_t* msg_len = nullptr; const uint32_t* order = nullptr;
   const uint32_t* cand_body = nullptr; const uint32_t* cand_bh = nullptr;
@@ -270,6 +274,10 @@ struct Chunk {  // host view of one chunk
   const uint8_t* span_host = nullptr;
   size_t span_bytes = 0, o_canon = 0;
   uint32_t n_canon = 0;
+  // device front end (frontend.cuh): headers parsed / preimages built / base64 decoded on the device too
+  bool fe = false;
+  size_t o_fein = 0;
+  std::vector<FeIn> fein_host;   // kept for result resolution (raw offsets of the emails)
 };
 
 struct Slot {
@@ -591,12 +599,68 @@ void process_email(ThreadCtx& c, const zkb_email_view& em, bool want_regex, int 
   else { rec.key_msg = c.add_msg(em.key, em.key_len); c.key_msgs.emplace(key_id, rec.key_msg); }
 }
 
+// Device-front-end mode: the host only resolves the key, stages distinct domains / keys for hashing and
+// reserves slots; everything that reads the message bytes happens on the device (frontend.cuh).
+void process_email_fe(ThreadCtx& c, const zkb_email_view& em, uint32_t local_idx, int tid, EmailRec& rec) {
+  rec = EmailRec();
+  rec.tid = (uint32_t)tid;
+  rec.canon_rc = 0;
+  if (em.raw_email_len > 0xFFFFFF00u) { rec.status = ZKB_ST_MAIL_PARSE; return; }
+  int32_t key_id = -1;
+  KeyMeta km = KeyMeta();
+  if (em.key_type_len == 3 && memcmp(em.key_type, "rsa", 3) == 0) {
+    key_id = lookup_key(c, em.key, em.key_len, km);
+    if (key_id < 0) { rec.status = ZKB_ST_KEY; return; }
+  } else if (em.key_type_len == 7 && memcmp(em.key_type, "ed25519", 7) == 0) {
+    rec.status = em.key_len == 32 ? ZKB_ST_UNSUPPORTED : ZKB_ST_KEY;
+    return;
+  } else { rec.status = ZKB_ST_KEY; return; }
+  if (c.have_last_dom && c.last_dom.size() == em.from_domain_len && memcmp(c.last_dom.data(), em.from_domain, em.from_domain_len) == 0) rec.dom_msg = c.last_dom_msg;
+  else {
+    std::string d(em.from_domain, em.from_domain_len);
+    auto it = c.dom_msgs.find(d);
+    if (it != c.dom_msgs.end()) rec.dom_msg = it->second;
+    else { rec.dom_msg = c.add_msg((const uint8_t*)em.from_domain, em.from_domain_len); c.dom_msgs.emplace(d, rec.dom_msg); }
+    c.last_dom.swap(d); c.last_dom_msg = rec.dom_msg; c.have_last_dom = true;
+  }
+  auto kt = c.key_msgs.find(key_id);
+  if (kt != c.key_msgs.end()) rec.key_msg = kt->second;
+  else { rec.key_msg = c.add_msg(em.key, em.key_len); c.key_msgs.emplace(key_id, rec.key_msg); }
+  // slots: canonical body (<= raw + 2) and header preimage (FE_PRE_CAP), both device-only
+  CandRec cd;
+  memset(&cd, 0, sizeof cd);
+  cd.key_id = key_id; cd.algo = 1; cd.sig_state = SIG_OK; cd.rsa_list = (uint8_t)rsa_list_of(km);
+  auto virt_msg = [&](size_t cap_len, uint32_t est_len) {
+    MsgRec m;
+    m.goff = 0; m.len = est_len; m.blk = VIRT_BLK; m.local = (uint32_t)c.tr->virt_used; m.canon = 0;
+    c.tr->virt_used += ((cap_len >> 6) + 1) << 6;
+    c.tr->msgs.push_back(m);
+    const uint32_t nb = (est_len >> 6) + 1 + ((est_len & 63) >= 56 ? 1u : 0u);
+    if (c.tr->hist.size() <= nb) c.tr->hist.resize((size_t)nb + 1, 0u);
+    c.tr->hist[nb]++;
+    c.tr->sha_blocks += nb; c.tr->sha_bytes += est_len;
+    return (uint32_t)c.tr->msgs.size() - 1;
+  };
+  const uint32_t hdr_est = 640;   // ordering / statistics estimate; the device writes the real lengths
+  cd.body_msg = virt_msg(em.raw_email_len + 2, em.raw_email_len > hdr_est + 400 ? (uint32_t)em.raw_email_len - hdr_est - 400 : 64);
+  cd.hdr_msg = virt_msg(FE_PRE_CAP + 64, hdr_est);
+  cd.sig_off = (uint32_t)c.tr->sigw.size();
+  c.tr->sigw.resize(c.tr->sigw.size() + km.limbs_class, 0u);
+  c.tr->rsa_cnt[cd.rsa_list]++;
+  rec.fe_cand = (uint32_t)c.tr->cands.size();
+  rec.canon_cand = rec.fe_cand;
+  c.tr->cands.push_back(cd);
+  c.tr->fe_emails.push_back(local_idx);
+  (void)km;
+}
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 double g_prof_parse = 0, g_prof_layout = 0;  // ZKB_PROFILE accounting (single caller per engine)
 inline double now_s2() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // Host pack of emails [e0, e0+ne): parallel parse + layout of the SoA meta buffers.
-int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne, const zkb_regex_set* rs, Chunk& ch, PinBuf& pin_meta) {
+int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne, const zkb_regex_set* rs, Chunk& ch, PinBuf& pin_meta,
+               bool allow_fe = false) {
   const int T = e->pool->size();
   ch.e0 = e0; ch.ne = ne;
   ch.emails.assign(ne, EmailRec());
@@ -628,6 +692,7 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
       }
     }
   }
+  ch.fe = ch.direct && allow_fe && !getenv("ZKB_NO_DEVICE_FRONTEND");
   const size_t grain = std::max<size_t>(16, std::min<size_t>(512, ne / (size_t)(T * 8) + 1));
   e->pool->run([&](int tid) {
     ThreadCtx c;
@@ -638,7 +703,8 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
       if (lo >= ne) break;
       size_t hi = std::min(ne, lo + grain);
       for (size_t i = lo; i < hi; i++) {
-        process_email(c, emails[e0 + i], want_regex, tid, ch.emails[i]);
+        if (ch.fe) process_email_fe(c, emails[e0 + i], (uint32_t)i, tid, ch.emails[i]);
+        else process_email(c, emails[e0 + i], want_regex, tid, ch.emails[i]);
         if (c.oom) { oom = 1; return; }
       }
     }
@@ -692,8 +758,12 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
   ch.o_sig = o; o += align_up(sig_words * 4, 16);
   for (int k = 0; k < 6; k++) { ch.o_rsa[k] = o; ch.rsa_n[k] = rn[k]; o += align_up((size_t)rn[k] * sizeof(RsaItem), 16); }
   ch.o_dfa = o; o += align_up((size_t)n_dfa * 2 * sizeof(DfaItem), 16);  // header haystack + body haystack per email
+  if (ch.fe) NC = C;   // device front end: one canon item per candidate, written by the device
+  ch.n_canon = NC;
   ch.o_canon = o; o += align_up((size_t)NC * sizeof(CanonItem), 16);
+  ch.o_fein = o; o += align_up(ch.fe ? (size_t)C * sizeof(FeIn) : 0, 16);
   ch.meta_bytes = o + 16;
+  if (ch.fe) ch.fein_host.assign(C, FeIn());
   if (!pin_meta.ensure(ch.meta_bytes)) return ZKB_E_NOMEM;
   uint8_t* mh = pin_meta.p;  // every array below is written in full; padding bytes are never read
   uint64_t* msg_off = (uint64_t*)(mh + ch.o_msg_off);
@@ -733,6 +803,27 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
     if (!t.sigw.empty()) memcpy(sigw + sig_base[tid], t.sigw.data(), t.sigw.size() * 4);
     CanonItem* ci = (CanonItem*)(mh + ch.o_canon) + t.canon_base;
     for (size_t i = 0; i < t.canon.size(); i++) { ci[i] = t.canon[i]; ci[i].msg += t.msg_base; }
+    if (ch.fe) {
+      FeIn* fin = (FeIn*)(mh + ch.o_fein);
+      for (size_t j = 0; j < t.fe_emails.size(); j++) {
+        const zkb_email_view& em = emails[e0 + t.fe_emails[j]];
+        const EmailRec& er = ch.emails[t.fe_emails[j]];
+        const CandRec& cd = t.cands[j];
+        const KeyMeta& km = e->key_meta[cd.key_id];
+        FeIn fi;
+        memset(&fi, 0, sizeof fi);
+        fi.raw_off = (uint64_t)(em.raw_email - ch.span_host);
+        fi.raw_len = (uint32_t)em.raw_email_len;
+        fi.dom_off = (uint32_t)t.msgs[er.dom_msg].goff;   // staged domains sit at the front of the arena (< 4 GiB)
+        fi.dom_len = (uint32_t)em.from_domain_len;
+        fi.k = km.k; fi.limbs = km.limbs_class;
+        fi.sig_word_off = (uint32_t)(sig_base[tid] + cd.sig_off);
+        fi.body_msg = t.msg_base + cd.body_msg; fi.pre_msg = t.msg_base + cd.hdr_msg;
+        fi.cand = t.cand_base + (uint32_t)j;
+        fin[t.cand_base + j] = fi;
+        ch.fein_host[t.cand_base + j] = fi;
+      }
+    }
   });
   // DFA items: for each email with haystacks, slot 2*j = header preimage, 2*j+1 = canonical body
   uint64_t dfa_bytes = 0;
@@ -768,10 +859,12 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
   return ZKB_OK;
 }
 
-size_t out_layout(uint32_t M, uint32_t C, size_t ne, size_t P, size_t& o_flags, size_t& o_dfa) {
+size_t out_layout(uint32_t M, uint32_t C, size_t ne, size_t P, size_t& o_flags, size_t& o_dfa, size_t n_fe = 0, size_t* o_fe = nullptr) {
   size_t o = align_up((size_t)M * 32, 16);
   o_flags = o; o += align_up((size_t)C * 4, 16);
   o_dfa = o; o += ne * P * 16;
+  if (o_fe) *o_fe = o;
+  o += n_fe * sizeof(FeOut);
   return o + 16;
 }
 
@@ -779,14 +872,14 @@ size_t out_layout(uint32_t M, uint32_t C, size_t ne, size_t P, size_t& o_flags, 
 int upload_chunk(zkb_engine* e, Chunk& ch, const zkb_regex_set* rs, DeviceChunk& d, PinBuf& pin_meta, cudaStream_t stream) {
   const size_t P = rs ? rs->n_active() : 0;
   if (!d.arena.ensure(ch.arena_bytes) || !d.meta.ensure(ch.meta_bytes)) return ZKB_E_NOMEM;
-  size_t o_flags, o_dfa;
-  d.out_bytes = out_layout(ch.M, ch.C, ch.ne, P, o_flags, o_dfa);
+  size_t o_flags, o_dfa, o_fe = 0;
+  d.out_bytes = out_layout(ch.M, ch.C, ch.ne, P, o_flags, o_dfa, ch.fe ? ch.C : 0, &o_fe);
   if (!d.out.ensure(d.out_bytes)) return ZKB_E_NOMEM;
   for (auto& t : ch.tr)
     for (auto& b : t.blocks)
       if (b.used) CK(cudaMemcpyAsync(d.arena.p + b.dev_off, b.p, b.used, cudaMemcpyHostToDevice, stream));
   CK(cudaMemcpyAsync(d.meta.p, pin_meta.p, ch.meta_bytes, cudaMemcpyHostToDevice, stream));
-  d.n_canon = 0;
+  d.n_canon = 0; d.n_fe = 0;
   if (ch.direct && ch.n_canon) {
     if (!d.span.ensure(ch.span_bytes + 256)) return ZKB_E_NOMEM;
     CK(cudaMemcpyAsync(d.span.p, ch.span_host, ch.span_bytes, cudaMemcpyHostToDevice, stream));  // DMA from registered memory
@@ -794,6 +887,14 @@ int upload_chunk(zkb_engine* e, Chunk& ch, const zkb_regex_set* rs, DeviceChunk&
     d.n_canon = ch.n_canon;
   }
   d.msg_len_rw = (uint32_t*)(d.meta.p + ch.o_msg_len);
+  if (ch.fe && ch.C) {
+    d.fe_in = (const FeIn*)(d.meta.p + ch.o_fein);
+    d.fe_out = (FeOut*)(d.out.p + o_fe);
+    d.n_fe = ch.C;
+    d.canon_rw = (CanonItem*)(d.meta.p + ch.o_canon);
+    d.cand_bh_rw = (uint32_t*)(d.meta.p + ch.o_cand_bh);
+    d.sig_rw = (uint32_t*)(d.meta.p + ch.o_sig);
+  }
   CK(cudaMemsetAsync(d.out.p + o_flags, 0, align_up((size_t)ch.C * 4, 16), stream));
   if (P) CK(cudaMemsetAsync(d.out.p + o_dfa, 0, ch.ne * P * 16, stream));
   d.msg_off = (const uint64_t*)(d.meta.p + ch.o_msg_off);
@@ -835,6 +936,10 @@ int sync_keytab(zkb_engine* e, cudaStream_t stream) {
 // Enqueues every kernel of one chunk.  ev (optional): 5 events recorded around the kernel families.
 int launch_chunk(zkb_engine* e, const DeviceChunk& d, const zkb_regex_set* rs, cudaStream_t s, cudaEvent_t* ev, uint64_t* launches) {
   uint64_t nl = 0;
+  if (d.n_fe) {
+    launch_frontend(d.span.p, d.fe_in, d.n_fe, d.arena.p, d.msg_off, d.msg_len_rw, d.sig_rw, d.cand_bh_rw, d.canon_rw, d.fe_out, s);
+    nl++;
+  }
   if (d.n_canon) { launch_canon_body(d.span.p, d.canon_items, d.n_canon, d.arena.p, d.msg_off, d.msg_len_rw, s); nl++; }
   if (ev) CK(cudaEventRecord(ev[0], s));
   if (d.M) { launch_sha256(d.arena.p, d.msg_off, d.msg_len, d.order, d.M, d.digests, s); nl++; }
@@ -978,15 +1083,107 @@ void resolve_email(const zkb_engine* e, const Chunk& ch, size_t i, const uint8_t
   }
 }
 
+// Device-front-end mode.  Returns false when the device declined the message (the caller re-runs it
+// through the host front end); otherwise fills the record exactly as resolve_email would.
+bool resolve_email_fe(const zkb_engine* e, const Chunk& ch, size_t i, const uint8_t* outp, size_t o_flags, size_t o_dfa, size_t o_fe,
+                      const zkb_regex_set* rs, const zkb_email_captures* caps, std::vector<uint8_t>& scratch,
+                      zkb_result& res, std::string& s1, std::string& s2) {
+  memset(&res, 0, rs ? sizeof res : offsetof(zkb_result, parts));
+  res.dkim_detail = ZKB_DKIM_NEUTRAL;
+  const EmailRec& er = ch.emails[i];
+  if (er.status != ZKB_ST_OK) { res.status = er.status; return true; }
+  const ThreadRecs& t = ch.tr[er.tid];
+  const uint32_t gc = t.cand_base + er.fe_cand;
+  const FeOut& fo = ((const FeOut*)(outp + o_fe))[gc];
+  if (fo.flags & FE_MAIL_PARSE) { res.status = ZKB_ST_MAIL_PARSE; return true; }
+  if (fo.flags & FE_FALLBACK) return false;
+  const CandRec& cd = t.cands[er.fe_cand];
+  const uint32_t* digests = (const uint32_t*)outp;
+  const uint32_t f = ((const uint32_t*)(outp + o_flags))[gc];
+  auto put_digest = [&](uint8_t* dst, uint32_t gmsg) {
+    const uint32_t* w = digests + (size_t)gmsg * 8;
+    for (int k = 0; k < 8; k++) { dst[4 * k] = (uint8_t)(w[k] >> 24); dst[4 * k + 1] = (uint8_t)(w[k] >> 16); dst[4 * k + 2] = (uint8_t)(w[k] >> 8); dst[4 * k + 3] = (uint8_t)w[k]; }
+  };
+  put_digest(res.body_hash, t.msg_base + cd.body_msg);
+  put_digest(res.header_hash, t.msg_base + cd.hdr_msg);
+  res.bh_ok = ((fo.flags & FE_BH_VALID) && (f & ZKB_F_BH_OK)) ? 1 : 0;
+  int detail = ZKB_DKIM_PASS;
+  if (!res.bh_ok) detail = ZKB_DKIM_BODY_HASH;
+  else if (fo.flags & FE_SIG_SYNTAX) detail = ZKB_DKIM_SIG_SYNTAX;
+  else if ((fo.flags & FE_SIG_BADLEN) || !(f & ZKB_F_RSA_OK)) detail = ZKB_DKIM_SIG_MISMATCH;
+  res.dkim_detail = detail;
+  if (detail != ZKB_DKIM_PASS) { res.status = ZKB_ST_DKIM_FAIL; return true; }
+  res.rsa_ok = 1;
+  put_digest(res.from_domain_hash, t.msg_base + er.dom_msg);
+  put_digest(res.public_key_hash, t.msg_base + er.key_msg);
+  if (!rs) return true;
+  const size_t P = rs->n_active();
+  const uint4* dfa = (const uint4*)(outp + o_dfa) + i * P;
+  const FeIn& fi = ch.fein_host[gc];
+  const uint8_t* raw = ch.span_host + fi.raw_off;
+  size_t pi = 0;
+  for (size_t p = 0; p < rs->parts.size(); p++) {
+    const bool body = rs->parts[p].body;
+    if (body ? !rs->body_present : !rs->header_present) continue;
+    const uint4 r = dfa[pi++];
+    uint32_t slot = res.n_parts;
+    if (slot < ZKB_MAX_PARTS) {
+      res.parts[slot].match_count = r.x; res.parts[slot].start = r.y; res.parts[slot].end = r.z; res.parts[slot].captures_ok = 0;
+      res.n_parts++;
+    }
+    bool ok = r.x == 1;
+    if (ok && caps) {
+      const zkb_email_captures& ec = caps[ch.e0 + i];
+      bool loaded = false;
+      for (size_t q = 0; q < ec.n_caps && ok; q++) {
+        if (ec.caps[q].part != p) continue;
+        if (!loaded) {  // rebuild the haystack on the host from the raw message (only emails with captures pay)
+          HayView hv;
+          if (body) {
+            scratch.resize((size_t)fo.body_len + 64);
+            size_t cl = (fo.flags & FE_BODY_RELAXED) ? canon_body_relaxed(raw + fo.body_off, fo.body_len, scratch.data())
+                                                     : canon_body_simple(raw + fo.body_off, fo.body_len, scratch.data());
+            hv.p = scratch.data(); hv.n = (uint32_t)cl;
+          } else {
+            uint8_t *hp = nullptr, *bp = nullptr;
+            size_t hl = 0, bl = 0;
+            int detail2 = 0;
+            if (zkb_host_canonicalize(raw, fi.raw_len, e->now_unix, &hp, &hl, &bp, &bl, &detail2) != ZKB_OK) { ok = false; break; }
+            scratch.assign(hp, hp + hl);
+            free(hp); free(bp);
+            hv.p = scratch.data(); hv.n = (uint32_t)hl;
+          }
+          cleaned_span(hv, body, r.y, r.z, s1);
+          bool ascii = true;
+          for (char ch2 : s1) if (ch2 & 0x80) { ascii = false; break; }
+          if (!ascii) { utf8_lossy((const uint8_t*)s1.data(), s1.size(), s2); s1.swap(s2); }
+          loaded = true;
+        }
+        if (ec.caps[q].len && s1.find(ec.caps[q].s, 0, ec.caps[q].len) == std::string::npos) ok = false;
+      }
+    }
+    if (ok && slot < ZKB_MAX_PARTS) res.parts[slot].captures_ok = 1;
+    if (!ok) { res.status = body ? ZKB_ST_REGEX_BODY : ZKB_ST_REGEX_HEADER; return true; }
+  }
+  return true;
+}
+
+// fallback (optional): chunk-local indices of the messages the device front end declined
 void resolve_chunk(zkb_engine* e, const Chunk& ch, const uint8_t* outp, const zkb_regex_set* rs, const zkb_email_captures* caps,
-                   zkb_result* out) {
+                   zkb_result* out, std::vector<size_t>* fallback = nullptr) {
   const size_t P = rs ? rs->n_active() : 0;
-  size_t o_flags, o_dfa;
-  out_layout(ch.M, ch.C, ch.ne, P, o_flags, o_dfa);
+  size_t o_flags, o_dfa, o_fe = 0;
+  out_layout(ch.M, ch.C, ch.ne, P, o_flags, o_dfa, ch.fe ? ch.C : 0, &o_fe);
+  std::mutex fb_mu;
   e->pool->parallel_for(ch.ne, 256, [&](size_t lo, size_t hi, int) {
     std::string s1, s2;
     std::vector<uint8_t> scratch;
-    for (size_t i = lo; i < hi; i++) resolve_email(e, ch, i, outp, o_flags, o_dfa, rs, caps, scratch, out[ch.e0 + i], s1, s2);
+    std::vector<size_t> local_fb;
+    for (size_t i = lo; i < hi; i++) {
+      if (!ch.fe) { resolve_email(e, ch, i, outp, o_flags, o_dfa, rs, caps, scratch, out[ch.e0 + i], s1, s2); continue; }
+      if (!resolve_email_fe(e, ch, i, outp, o_flags, o_dfa, o_fe, rs, caps, scratch, out[ch.e0 + i], s1, s2)) local_fb.push_back(ch.e0 + i);
+    }
+    if (!local_fb.empty() && fallback) { std::lock_guard<std::mutex> l(fb_mu); fallback->insert(fallback->end(), local_fb.begin(), local_fb.end()); }
   });
 }
 
@@ -1157,12 +1354,8 @@ static double now_s() {
 }
 
 // Pipelined end-to-end batch: pack chunk k+1 on the host while chunk k is on the device.
-int zkb_verify_batch(zkb_engine* e, const zkb_email_view* emails, size_t n, const zkb_regex_set* regex,
-                     const zkb_email_captures* captures, zkb_result* out) {
-  if (!e || (!emails && n) || (!out && n)) return ZKB_E_INVALID;
-  if (regex && regex->eng != e) return ZKB_E_INVALID;
-  std::lock_guard<std::mutex> lock(e->run_mu);
-  CK(cudaSetDevice(e->device));
+static int verify_batch_impl(zkb_engine* e, const zkb_email_view* emails, size_t n, const zkb_regex_set* regex,
+                             const zkb_email_captures* captures, zkb_result* out, bool allow_fe, std::vector<size_t>* fallback) {
   const std::vector<size_t> bounds = chunk_bounds(emails, n, e->chunk_emails, (size_t)192 << 20);
   const size_t nchunks = bounds.size() - 1;
   Chunk chunks[3];
@@ -1178,7 +1371,7 @@ int zkb_verify_batch(zkb_engine* e, const zkb_email_view* emails, size_t n, cons
     CK(cudaEventSynchronize(s.done));
     double tb = now_s();
     t_wait += tb - ta;
-    resolve_chunk(e, ch, s.result.p, regex, captures, out);
+    resolve_chunk(e, ch, s.result.p, regex, captures, out, fallback);
     release_blocks(e, ch);
     busy[si] = false;
     t_resolve += now_s() - tb;
@@ -1193,7 +1386,7 @@ int zkb_verify_batch(zkb_engine* e, const zkb_email_view* emails, size_t n, cons
     Chunk& ch = chunks[si];
     size_t e0 = bounds[k], ne = bounds[k + 1] - bounds[k];
     double t0 = now_s();
-    rc = pack_chunk(e, emails, e0, ne, regex, ch, s.meta);
+    rc = pack_chunk(e, emails, e0, ne, regex, ch, s.meta, allow_fe);
     if (rc) break;
     double t1 = now_s();
     t_pack += t1 - t0;
@@ -1224,6 +1417,29 @@ int zkb_verify_batch(zkb_engine* e, const zkb_email_view* emails, size_t n, cons
             n, nchunks, e->pool->size(), 1e3 * (now_s() - t_all), 1e3 * t_pack, 1e3 * g_prof_parse, 1e3 * g_prof_layout, 1e3 * t_upload,
             1e3 * t_wait, 1e3 * t_resolve);
   return rc;
+}
+
+int zkb_verify_batch(zkb_engine* e, const zkb_email_view* emails, size_t n, const zkb_regex_set* regex,
+                     const zkb_email_captures* captures, zkb_result* out) {
+  if (!e || (!emails && n) || (!out && n)) return ZKB_E_INVALID;
+  if (regex && regex->eng != e) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lock(e->run_mu);
+  CK(cudaSetDevice(e->device));
+  std::vector<size_t> fb;
+  int rc = verify_batch_impl(e, emails, n, regex, captures, out, true, &fb);
+  if (rc || fb.empty()) return rc;
+  // messages the device front end declined (irregular structure): the host front end implements every path
+  std::sort(fb.begin(), fb.end());
+  std::vector<zkb_email_view> v2(fb.size());
+  std::vector<zkb_email_captures> c2(captures ? fb.size() : 0);
+  std::vector<zkb_result> r2(fb.size());
+  for (size_t i = 0; i < fb.size(); i++) { v2[i] = emails[fb[i]]; if (captures) c2[i] = captures[fb[i]]; }
+  rc = verify_batch_impl(e, v2.data(), v2.size(), regex, captures ? c2.data() : nullptr, r2.data(), false, nullptr);
+  if (rc) return rc;
+  const size_t rec_bytes = regex ? sizeof(zkb_result) : offsetof(zkb_result, parts);
+  for (size_t i = 0; i < fb.size(); i++) memcpy(&out[fb[i]], &r2[i], rec_bytes);
+  if (getenv("ZKB_PROFILE")) fprintf(stderr, "[zkb profile] device front end declined %zu of %zu messages (host front end used)\n", fb.size(), n);
+  return ZKB_OK;
 }
 
 int zkb_verify_one(zkb_engine* e, const zkb_email_view* email, const zkb_regex_set* regex, const zkb_email_captures* captures,
