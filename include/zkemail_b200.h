@@ -170,6 +170,9 @@ int zkb_batch_get_stats(const zkb_batch *b, zkb_batch_stats *out);
  * the engine stream: [0]=sha256 [1]=rsa [2]=dfa [3]=bh/finalize [4]=whole run */
 int zkb_batch_last_timing(const zkb_batch *b, float ms[5]);
 void *zkb_engine_stream(zkb_engine *e);          /* cudaStream_t of the engine */
+/* Bytes the last zkb_verify_batch moved host->device / device->host, and how many of its messages the
+ * device front end declined (re-run through the host front end). */
+int zkb_engine_last_batch_bytes(const zkb_engine *e, uint64_t *h2d, uint64_t *d2h, uint64_t *host_front_end_emails);
 /* Device-resident verdict words of chunk `chunk` of a prepared batch (one u32 per signature candidate:
  * bit0 = RSA ok, bit1 = bh= ok), for the multi-GPU all-gather of verdict bits over NCCL without a
  * host round trip.  *n_chunks (optional) receives the number of chunks.  Valid until the batch is

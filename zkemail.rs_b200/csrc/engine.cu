@@ -227,6 +227,7 @@ struct ThreadRecs {
   std::vector<uint32_t> sigw;
   std::vector<CanonItem> canon;     // bodies to canonicalise on the device (direct mode)
   std::vector<uint32_t> fe_emails;  // device-front-end mode: chunk-local email index of candidate j
+  size_t fe_sig_words = 0;          // device-front-end mode: signature limbs are written by the device only
   uint64_t virt_used = 0, virt_base = 0;   // device-only arena region of this thread (canonical body slots)
   uint32_t canon_base = 0;
   std::vector<uint32_t> hist;       // messages per SHA block count (maintained by commit)
@@ -235,7 +236,7 @@ struct ThreadRecs {
   uint32_t msg_base = 0, cand_base = 0;
   void clear() {
     msgs.clear(); cands.clear(); steps.clear(); sigw.clear(); hist.clear(); canon.clear(); fe_emails.clear();
-    virt_used = 0;
+    virt_used = 0; fe_sig_words = 0;
     sha_blocks = sha_bytes = 0;
     for (auto& c : rsa_cnt) c = 0;
   }
@@ -277,7 +278,8 @@ struct Chunk {  // host view of one chunk
   // device front end (frontend.cuh): headers parsed / preimages built / base64 decoded on the device too
   bool fe = false;
   size_t o_fein = 0;
-  std::vector<FeIn> fein_host;   // kept for result resolution (raw offsets of the emails)
+  const zkb_email_view* views = nullptr;   // the caller's views of this chunk (borrowed for the call)
+  size_t upload_bytes = 0;                 // leading part of the meta buffer that is copied host -> device
 };
 
 struct Slot {
@@ -317,6 +319,7 @@ struct zkb_engine {
   uint32_t* d_keytab = nullptr;
   size_t d_keytab_cap = 0, d_keytab_n = 0;
   cudaEvent_t ev[8] = {nullptr};
+  uint64_t last_h2d = 0, last_d2h = 0, last_fallback = 0;   // of the last zkb_verify_batch
 };
 
 struct zkb_batch {
@@ -345,10 +348,12 @@ struct ThreadCtx {
   std::vector<uint8_t> tmp;
   std::unordered_map<std::string, std::pair<int32_t, KeyMeta>> key_cache;
   struct PtrKey { const uint8_t* p = nullptr; size_t len = 0; int32_t id = 0; KeyMeta meta; };
-  PtrKey ptr_cache[64];  // same buffer => same bytes: skips the content hash for pooled keys
+  PtrKey ptr_cache[256];  // same buffer => same bytes: skips the content hash for pooled keys
+  static size_t ptr_slot(const void* p) { return (size_t)(((uint64_t)(uintptr_t)p * 0x9E3779B97F4A7C15ull) >> 56); }
+  struct PtrDom { const char* p = nullptr; size_t len = 0; uint32_t msg = 0; };
+  PtrDom dom_cache[256];
   std::unordered_map<std::string, uint32_t> dom_msgs;
   std::unordered_map<int32_t, uint32_t> key_msgs;
-  std::string last_dom; uint32_t last_dom_msg = 0; bool have_last_dom = false;
   bool oom = false;
   bool direct = false;                 // bodies are canonicalised on the device from the raw span
   const uint8_t* span_host = nullptr;
@@ -410,7 +415,7 @@ struct ThreadCtx {
 };
 
 int32_t lookup_key(ThreadCtx& c, const uint8_t* der, size_t len, KeyMeta& meta) {
-  ThreadCtx::PtrKey& pk = c.ptr_cache[((uintptr_t)der >> 4) & 63];
+  ThreadCtx::PtrKey& pk = c.ptr_cache[ThreadCtx::ptr_slot(der)];
   if (pk.p == der && pk.len == len) { meta = pk.meta; return pk.id; }
   std::string k((const char*)der, len);
   auto it = c.key_cache.find(k);
@@ -586,13 +591,14 @@ void process_email(ThreadCtx& c, const zkb_email_view& em, bool want_regex, int 
   }
   rec.n_steps = (uint32_t)c.tr->steps.size() - rec.first_step;
   // from_domain / key hashes (circuits.rs:16-17), one message per distinct value and thread
-  if (c.have_last_dom && c.last_dom.size() == em.from_domain_len && memcmp(c.last_dom.data(), em.from_domain, em.from_domain_len) == 0) rec.dom_msg = c.last_dom_msg;
+  ThreadCtx::PtrDom& pd = c.dom_cache[ThreadCtx::ptr_slot(em.from_domain)];
+  if (pd.p == em.from_domain && pd.len == em.from_domain_len && pd.p) rec.dom_msg = pd.msg;
   else {
     std::string d(em.from_domain, em.from_domain_len);
     auto it = c.dom_msgs.find(d);
     if (it != c.dom_msgs.end()) rec.dom_msg = it->second;
-    else { rec.dom_msg = c.add_msg((const uint8_t*)em.from_domain, em.from_domain_len); c.dom_msgs.emplace(d, rec.dom_msg); }
-    c.last_dom.swap(d); c.last_dom_msg = rec.dom_msg; c.have_last_dom = true;
+    else { rec.dom_msg = c.add_msg((const uint8_t*)em.from_domain, em.from_domain_len); c.dom_msgs.emplace(std::move(d), rec.dom_msg); }
+    pd.p = em.from_domain; pd.len = em.from_domain_len; pd.msg = rec.dom_msg;
   }
   auto kt = c.key_msgs.find(key_id);
   if (kt != c.key_msgs.end()) rec.key_msg = kt->second;
@@ -615,13 +621,14 @@ void process_email_fe(ThreadCtx& c, const zkb_email_view& em, uint32_t local_idx
     rec.status = em.key_len == 32 ? ZKB_ST_UNSUPPORTED : ZKB_ST_KEY;
     return;
   } else { rec.status = ZKB_ST_KEY; return; }
-  if (c.have_last_dom && c.last_dom.size() == em.from_domain_len && memcmp(c.last_dom.data(), em.from_domain, em.from_domain_len) == 0) rec.dom_msg = c.last_dom_msg;
+  ThreadCtx::PtrDom& pd = c.dom_cache[ThreadCtx::ptr_slot(em.from_domain)];
+  if (pd.p == em.from_domain && pd.len == em.from_domain_len && pd.p) rec.dom_msg = pd.msg;
   else {
     std::string d(em.from_domain, em.from_domain_len);
     auto it = c.dom_msgs.find(d);
     if (it != c.dom_msgs.end()) rec.dom_msg = it->second;
-    else { rec.dom_msg = c.add_msg((const uint8_t*)em.from_domain, em.from_domain_len); c.dom_msgs.emplace(d, rec.dom_msg); }
-    c.last_dom.swap(d); c.last_dom_msg = rec.dom_msg; c.have_last_dom = true;
+    else { rec.dom_msg = c.add_msg((const uint8_t*)em.from_domain, em.from_domain_len); c.dom_msgs.emplace(std::move(d), rec.dom_msg); }
+    pd.p = em.from_domain; pd.len = em.from_domain_len; pd.msg = rec.dom_msg;
   }
   auto kt = c.key_msgs.find(key_id);
   if (kt != c.key_msgs.end()) rec.key_msg = kt->second;
@@ -644,8 +651,8 @@ void process_email_fe(ThreadCtx& c, const zkb_email_view& em, uint32_t local_idx
   const uint32_t hdr_est = 640;   // ordering / statistics estimate; the device writes the real lengths
   cd.body_msg = virt_msg(em.raw_email_len + 2, em.raw_email_len > hdr_est + 400 ? (uint32_t)em.raw_email_len - hdr_est - 400 : 64);
   cd.hdr_msg = virt_msg(FE_PRE_CAP + 64, hdr_est);
-  cd.sig_off = (uint32_t)c.tr->sigw.size();
-  c.tr->sigw.resize(c.tr->sigw.size() + km.limbs_class, 0u);
+  cd.sig_off = (uint32_t)c.tr->fe_sig_words;
+  c.tr->fe_sig_words += km.limbs_class;
   c.tr->rsa_cnt[cd.rsa_list]++;
   rec.fe_cand = (uint32_t)c.tr->cands.size();
   rec.canon_cand = rec.fe_cand;
@@ -662,7 +669,7 @@ inline double now_s2() { return std::chrono::duration<double>(std::chrono::stead
 int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne, const zkb_regex_set* rs, Chunk& ch, PinBuf& pin_meta,
                bool allow_fe = false) {
   const int T = e->pool->size();
-  ch.e0 = e0; ch.ne = ne;
+  ch.e0 = e0; ch.ne = ne; ch.views = emails + e0;
   ch.emails.assign(ne, EmailRec());
   ch.tr.resize(T);
   for (auto& t : ch.tr) t.clear();
@@ -720,7 +727,7 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
     for (auto& b : t.blocks) { b.dev_off = off; off += align_up(b.used, 128); }
     t.msg_base = M; t.cand_base = C; t.canon_base = NC;
     M += (uint32_t)t.msgs.size(); C += (uint32_t)t.cands.size(); NC += (uint32_t)t.canon.size();
-    sig_words += t.sigw.size();
+    sig_words += t.sigw.size() + t.fe_sig_words;
   }
   const uint64_t staged_bytes = off;   // what travels host -> device out of the staging blocks
   for (auto& t : ch.tr) { t.virt_base = off; off += align_up(t.virt_used, 128); }  // device-only canonical body slots
@@ -748,22 +755,24 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
   uint32_t n_dfa = 0;
   if (P) for (auto& er : ch.emails) if (er.status == ZKB_ST_OK && er.canon_rc == 0) n_dfa++;
   ch.n_dfa = n_dfa;
-  // meta offsets
+  // meta offsets.  In device-front-end mode the arrays the DEVICE writes (bh= words, signature limbs, canon
+  // items) go last and are not uploaded.
+  if (ch.fe) NC = C;   // one canon item per candidate, written by the device
+  ch.n_canon = NC;
   size_t o = 0;
   ch.o_msg_off = o; o += align_up((size_t)M * 8, 16);
   ch.o_msg_len = o; o += align_up((size_t)M * 4, 16);
   ch.o_order = o; o += align_up((size_t)M * 4, 16);
   ch.o_cand_body = o; o += align_up((size_t)C * 4, 16);
-  ch.o_cand_bh = o; o += align_up((size_t)C * 32, 16);
-  ch.o_sig = o; o += align_up(sig_words * 4, 16);
   for (int k = 0; k < 6; k++) { ch.o_rsa[k] = o; ch.rsa_n[k] = rn[k]; o += align_up((size_t)rn[k] * sizeof(RsaItem), 16); }
   ch.o_dfa = o; o += align_up((size_t)n_dfa * 2 * sizeof(DfaItem), 16);  // header haystack + body haystack per email
-  if (ch.fe) NC = C;   // device front end: one canon item per candidate, written by the device
-  ch.n_canon = NC;
-  ch.o_canon = o; o += align_up((size_t)NC * sizeof(CanonItem), 16);
   ch.o_fein = o; o += align_up(ch.fe ? (size_t)C * sizeof(FeIn) : 0, 16);
+  if (ch.fe) ch.upload_bytes = o;
+  ch.o_cand_bh = o; o += align_up((size_t)C * 32, 16);
+  ch.o_sig = o; o += align_up(sig_words * 4, 16);
+  ch.o_canon = o; o += align_up((size_t)NC * sizeof(CanonItem), 16);
   ch.meta_bytes = o + 16;
-  if (ch.fe) ch.fein_host.assign(C, FeIn());
+  if (!ch.fe) ch.upload_bytes = ch.meta_bytes;
   if (!pin_meta.ensure(ch.meta_bytes)) return ZKB_E_NOMEM;
   uint8_t* mh = pin_meta.p;  // every array below is written in full; padding bytes are never read
   uint64_t* msg_off = (uint64_t*)(mh + ch.o_msg_off);
@@ -773,7 +782,7 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
   uint32_t* cand_bh = (uint32_t*)(mh + ch.o_cand_bh);
   uint32_t* sigw = (uint32_t*)(mh + ch.o_sig);
   std::vector<size_t> sig_base(T, 0);
-  { size_t sb = 0; for (int t = 0; t < T; t++) { sig_base[t] = sb; sb += ch.tr[t].sigw.size(); } }
+  { size_t sb = 0; for (int t = 0; t < T; t++) { sig_base[t] = sb; sb += ch.tr[t].sigw.size() + ch.tr[t].fe_sig_words; } }
   // one parallel pass: every thread lays out the records it produced
   e->pool->run([&](int tid) {
     ThreadRecs& t = ch.tr[tid];
@@ -791,7 +800,7 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
     for (size_t i = 0; i < t.cands.size(); i++) {
       const CandRec& cd = t.cands[i];
       cand_body[t.cand_base + i] = t.msg_base + cd.body_msg;
-      memcpy(cand_bh + (size_t)(t.cand_base + i) * 8, cd.bh, 32);
+      if (!ch.fe) memcpy(cand_bh + (size_t)(t.cand_base + i) * 8, cd.bh, 32);
       if (cd.haystack_only || cd.sig_state != SIG_OK || cd.algo != 1) continue;
       RsaItem it;
       it.sig_off = (uint32_t)(sig_base[tid] + cd.sig_off);
@@ -821,7 +830,6 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
         fi.body_msg = t.msg_base + cd.body_msg; fi.pre_msg = t.msg_base + cd.hdr_msg;
         fi.cand = t.cand_base + (uint32_t)j;
         fin[t.cand_base + j] = fi;
-        ch.fein_host[t.cand_base + j] = fi;
       }
     }
   });
@@ -854,7 +862,7 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
   }
   ch.st.dfa_items = (uint64_t)n_dfa * P; ch.st.dfa_bytes = dfa_bytes;
   ch.st.arena_bytes = ch.arena_bytes;
-  ch.st.h2d_bytes = staged_bytes + ch.meta_bytes + (ch.direct ? ch.span_bytes : 0);
+  ch.st.h2d_bytes = staged_bytes + ch.upload_bytes + (ch.direct ? ch.span_bytes : 0);
   g_prof_layout += now_s2() - tp1;
   return ZKB_OK;
 }
@@ -878,7 +886,7 @@ int upload_chunk(zkb_engine* e, Chunk& ch, const zkb_regex_set* rs, DeviceChunk&
   for (auto& t : ch.tr)
     for (auto& b : t.blocks)
       if (b.used) CK(cudaMemcpyAsync(d.arena.p + b.dev_off, b.p, b.used, cudaMemcpyHostToDevice, stream));
-  CK(cudaMemcpyAsync(d.meta.p, pin_meta.p, ch.meta_bytes, cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(d.meta.p, pin_meta.p, ch.upload_bytes, cudaMemcpyHostToDevice, stream));
   d.n_canon = 0; d.n_fe = 0;
   if (ch.direct && ch.n_canon) {
     if (!d.span.ensure(ch.span_bytes + 256)) return ZKB_E_NOMEM;
@@ -1119,8 +1127,8 @@ bool resolve_email_fe(const zkb_engine* e, const Chunk& ch, size_t i, const uint
   if (!rs) return true;
   const size_t P = rs->n_active();
   const uint4* dfa = (const uint4*)(outp + o_dfa) + i * P;
-  const FeIn& fi = ch.fein_host[gc];
-  const uint8_t* raw = ch.span_host + fi.raw_off;
+  const zkb_email_view& view = ch.views[i];
+  const uint8_t* raw = view.raw_email;
   size_t pi = 0;
   for (size_t p = 0; p < rs->parts.size(); p++) {
     const bool body = rs->parts[p].body;
@@ -1148,7 +1156,7 @@ bool resolve_email_fe(const zkb_engine* e, const Chunk& ch, size_t i, const uint
             uint8_t *hp = nullptr, *bp = nullptr;
             size_t hl = 0, bl = 0;
             int detail2 = 0;
-            if (zkb_host_canonicalize(raw, fi.raw_len, e->now_unix, &hp, &hl, &bp, &bl, &detail2) != ZKB_OK) { ok = false; break; }
+            if (zkb_host_canonicalize(raw, view.raw_email_len, e->now_unix, &hp, &hl, &bp, &bl, &detail2) != ZKB_OK) { ok = false; break; }
             scratch.assign(hp, hp + hl);
             free(hp); free(bp);
             hv.p = scratch.data(); hv.n = (uint32_t)hl;
@@ -1292,6 +1300,14 @@ int zkb_host_unregister(zkb_engine* e, const void* p) {
   return ZKB_E_INVALID;
 }
 
+int zkb_engine_last_batch_bytes(const zkb_engine* e, uint64_t* h2d, uint64_t* d2h, uint64_t* host_front_end_emails) {
+  if (!e) return ZKB_E_INVALID;
+  if (h2d) *h2d = e->last_h2d;
+  if (d2h) *d2h = e->last_d2h;
+  if (host_front_end_emails) *host_front_end_emails = e->last_fallback;
+  return ZKB_OK;
+}
+
 void* zkb_engine_stream(zkb_engine* e) { return e ? (void*)e->slots[0].stream : nullptr; }
 
 int zkb_regex_set_create(zkb_engine* e, const zkb_dfa_view* parts, size_t n_header, size_t n_body, int header_present,
@@ -1396,6 +1412,7 @@ static int verify_batch_impl(zkb_engine* e, const zkb_email_view* emails, size_t
     if (rc) break;
     rc = launch_chunk(e, s.dev, regex, s.stream, nullptr, nullptr);
     if (rc) break;
+    e->last_h2d += ch.st.h2d_bytes; e->last_d2h += s.dev.out_bytes;
     if (!s.result.ensure(s.dev.out_bytes)) { rc = ZKB_E_NOMEM; break; }
     CK(cudaMemcpyAsync(s.result.p, s.dev.out.p, s.dev.out_bytes, cudaMemcpyDeviceToHost, s.stream));
     CK(cudaEventRecord(s.done, s.stream));
@@ -1426,7 +1443,9 @@ int zkb_verify_batch(zkb_engine* e, const zkb_email_view* emails, size_t n, cons
   std::lock_guard<std::mutex> lock(e->run_mu);
   CK(cudaSetDevice(e->device));
   std::vector<size_t> fb;
+  e->last_h2d = e->last_d2h = e->last_fallback = 0;
   int rc = verify_batch_impl(e, emails, n, regex, captures, out, true, &fb);
+  e->last_fallback = fb.size();
   if (rc || fb.empty()) return rc;
   // messages the device front end declined (irregular structure): the host front end implements every path
   std::sort(fb.begin(), fb.end());

@@ -143,7 +143,7 @@ EXPORTED_SYMBOLS = (
     "zkb_batch_destroy", "zkb_batch_get_stats", "zkb_batch_last_timing", "zkb_engine_stream",
     "zkb_regex_compile", "zkb_free", "zkb_sha256_batch", "zkb_rsa_verify_batch",
     "zkb_dfa_scan_batch", "zkb_int_pipe_peaks", "zkb_host_canonicalize", "zkb_batch_device_flags",
-    "zkb_host_register", "zkb_host_unregister",
+    "zkb_host_register", "zkb_host_unregister", "zkb_engine_last_batch_bytes",
 )
 
 _lib = None
@@ -191,6 +191,7 @@ def load_library():
     L.zkb_batch_get_stats.argtypes = [vp, C.POINTER(BatchStats)]
     L.zkb_batch_last_timing.argtypes = [vp, C.POINTER(C.c_float * 5)]
     L.zkb_batch_device_flags.argtypes = [vp, sz, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
+    L.zkb_engine_last_batch_bytes.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.zkb_host_register.argtypes = [vp, vp, sz]
     L.zkb_host_unregister.argtypes = [vp, vp]
     L.zkb_engine_stream.argtypes = [vp]
@@ -447,6 +448,11 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def last_batch_bytes(self) -> dict:
+        h, d, f = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(self.lib.zkb_engine_last_batch_bytes(self.handle, C.byref(h), C.byref(d), C.byref(f)), "zkb_engine_last_batch_bytes")
+        return {"h2d_bytes": h.value, "d2h_bytes": d.value, "host_front_end_emails": f.value}
 
     def register_host(self, array: np.ndarray):
         """Page-locks caller memory holding raw messages (zero-copy input path, zkb_host_register)."""
