@@ -287,6 +287,7 @@ struct Slot {
   PinBuf meta, result;
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
+  cudaEvent_t k0 = nullptr, k1 = nullptr, h0 = nullptr;   // ZKB_PROFILE: H2D start, kernels start / end
 };
 
 }  // namespace
@@ -662,12 +663,14 @@ void process_email_fe(ThreadCtx& c, const zkb_email_view& em, uint32_t local_idx
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-double g_prof_parse = 0, g_prof_layout = 0;  // ZKB_PROFILE accounting (single caller per engine)
+double g_prof_parse = 0, g_prof_layout = 0, g_prof_prelude = 0;
+std::atomic<uint64_t> g_prof_busy_ns{0};  // ZKB_PROFILE accounting (single caller per engine)
 inline double now_s2() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // Host pack of emails [e0, e0+ne): parallel parse + layout of the SoA meta buffers.
+// ctxs: one ThreadCtx per pool thread, alive for the whole API call (key lookups are cached across chunks)
 int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne, const zkb_regex_set* rs, Chunk& ch, PinBuf& pin_meta,
-               bool allow_fe = false) {
+               std::vector<ThreadCtx>& ctxs, bool allow_fe = false) {
   const int T = e->pool->size();
   ch.e0 = e0; ch.ne = ne; ch.views = emails + e0;
   ch.emails.assign(ne, EmailRec());
@@ -700,11 +703,16 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
     }
   }
   ch.fe = ch.direct && allow_fe && !getenv("ZKB_NO_DEVICE_FRONTEND");
+  g_prof_prelude += now_s2() - tp0;
   const size_t grain = std::max<size_t>(16, std::min<size_t>(512, ne / (size_t)(T * 8) + 1));
   e->pool->run([&](int tid) {
-    ThreadCtx c;
+    const double tb0 = now_s2();
+    ThreadCtx& c = ctxs[tid];
     c.eng = e; c.tr = &ch.tr[tid];
     c.direct = ch.direct; c.span_host = ch.span_host;
+    c.oom = false;
+    c.dom_msgs.clear(); c.key_msgs.clear();          // message indices are per chunk
+    for (auto& dslot : c.dom_cache) dslot.p = nullptr;
     for (;;) {
       size_t lo = next.fetch_add(grain);
       if (lo >= ne) break;
@@ -715,6 +723,7 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
         if (c.oom) { oom = 1; return; }
       }
     }
+    g_prof_busy_ns.fetch_add((uint64_t)((now_s2() - tb0) * 1e9));
   });
   if (oom) return ZKB_E_NOMEM;
   const double tp1 = now_s2();
@@ -1253,6 +1262,7 @@ int zkb_engine_create(const zkb_options* opt, zkb_engine** out) {
   for (auto& s : e->slots) {
     CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    CK(cudaEventCreate(&s.k0)); CK(cudaEventCreate(&s.k1)); CK(cudaEventCreate(&s.h0));
   }
   for (auto& ev : e->ev) CK(cudaEventCreate(&ev));
   if (ensure_dfa_attr(e)) return ZKB_E_CUDA;
@@ -1268,6 +1278,9 @@ void zkb_engine_destroy(zkb_engine* e) {
     s.dev.free(); s.meta.free(); s.result.free();
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
+    if (s.k0) cudaEventDestroy(s.k0);
+    if (s.k1) cudaEventDestroy(s.k1);
+    if (s.h0) cudaEventDestroy(s.h0);
   }
   for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
   if (e->d_keytab) cudaFree(e->d_keytab);
@@ -1372,14 +1385,16 @@ static double now_s() {
 // Pipelined end-to-end batch: pack chunk k+1 on the host while chunk k is on the device.
 static int verify_batch_impl(zkb_engine* e, const zkb_email_view* emails, size_t n, const zkb_regex_set* regex,
                              const zkb_email_captures* captures, zkb_result* out, bool allow_fe, std::vector<size_t>* fallback) {
-  const std::vector<size_t> bounds = chunk_bounds(emails, n, e->chunk_emails, (size_t)192 << 20);
+  const std::vector<size_t> bounds = chunk_bounds(emails, n, e->chunk_emails, (size_t)256 << 20);
   const size_t nchunks = bounds.size() - 1;
+  std::vector<ThreadCtx> ctxs(e->pool->size());
   Chunk chunks[3];
   bool busy[3] = {false, false, false};
   const size_t P = regex ? regex->n_active() : 0;
   const bool prof = getenv("ZKB_PROFILE") != nullptr;
   double t_pack = 0, t_upload = 0, t_wait = 0, t_resolve = 0, t_all = now_s();
-  g_prof_parse = g_prof_layout = 0;
+  double t_gpu_h2d = 0, t_gpu_kern = 0;   // device-side stream time (ms) of the copies / kernels, summed over chunks
+  g_prof_parse = g_prof_layout = g_prof_prelude = 0; g_prof_busy_ns = 0;
   auto finish = [&](int si) -> int {
     Slot& s = e->slots[si];
     Chunk& ch = chunks[si];
@@ -1387,6 +1402,11 @@ static int verify_batch_impl(zkb_engine* e, const zkb_email_view* emails, size_t
     CK(cudaEventSynchronize(s.done));
     double tb = now_s();
     t_wait += tb - ta;
+    if (prof) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, s.h0, s.k0) == cudaSuccess) t_gpu_h2d += ms;
+      if (cudaEventElapsedTime(&ms, s.k0, s.k1) == cudaSuccess) t_gpu_kern += ms;
+    }
     resolve_chunk(e, ch, s.result.p, regex, captures, out, fallback);
     release_blocks(e, ch);
     busy[si] = false;
@@ -1402,16 +1422,19 @@ static int verify_batch_impl(zkb_engine* e, const zkb_email_view* emails, size_t
     Chunk& ch = chunks[si];
     size_t e0 = bounds[k], ne = bounds[k + 1] - bounds[k];
     double t0 = now_s();
-    rc = pack_chunk(e, emails, e0, ne, regex, ch, s.meta, allow_fe);
+    rc = pack_chunk(e, emails, e0, ne, regex, ch, s.meta, ctxs, allow_fe);
     if (rc) break;
     double t1 = now_s();
     t_pack += t1 - t0;
     rc = sync_keytab(e, s.stream);
     if (rc) break;
+    if (prof) CK(cudaEventRecord(s.h0, s.stream));
     rc = upload_chunk(e, ch, regex, s.dev, s.meta, s.stream);
     if (rc) break;
+    if (prof) CK(cudaEventRecord(s.k0, s.stream));
     rc = launch_chunk(e, s.dev, regex, s.stream, nullptr, nullptr);
     if (rc) break;
+    if (prof) CK(cudaEventRecord(s.k1, s.stream));
     e->last_h2d += ch.st.h2d_bytes; e->last_d2h += s.dev.out_bytes;
     if (!s.result.ensure(s.dev.out_bytes)) { rc = ZKB_E_NOMEM; break; }
     CK(cudaMemcpyAsync(s.result.p, s.dev.out.p, s.dev.out_bytes, cudaMemcpyDeviceToHost, s.stream));
@@ -1430,9 +1453,10 @@ static int verify_batch_impl(zkb_engine* e, const zkb_email_view* emails, size_t
   }
   (void)P;
   if (prof)
-    fprintf(stderr, "[zkb profile] n=%zu chunks=%zu threads=%d total=%.1fms pack=%.1f (parse %.1f, layout %.1f) upload+launch=%.1f wait_gpu=%.1f resolve=%.1f\n",
-            n, nchunks, e->pool->size(), 1e3 * (now_s() - t_all), 1e3 * t_pack, 1e3 * g_prof_parse, 1e3 * g_prof_layout, 1e3 * t_upload,
-            1e3 * t_wait, 1e3 * t_resolve);
+    fprintf(stderr, "[zkb profile] n=%zu chunks=%zu threads=%d total=%.1fms pack=%.1f (parse %.1f [prelude %.1f, thread-busy %.1f], layout %.1f) upload+launch=%.1f wait_gpu=%.1f resolve=%.1f | stream time: h2d %.1f kernels %.1f\n",
+            n, nchunks, e->pool->size(), 1e3 * (now_s() - t_all), 1e3 * t_pack, 1e3 * g_prof_parse, 1e3 * g_prof_prelude,
+            1e-6 * (double)g_prof_busy_ns.load() / e->pool->size(), 1e3 * g_prof_layout, 1e3 * t_upload, 1e3 * t_wait, 1e3 * t_resolve,
+            t_gpu_h2d, t_gpu_kern);
   return rc;
 }
 
@@ -1486,13 +1510,14 @@ int zkb_batch_prepare(zkb_engine* e, const zkb_email_view* emails, size_t n, con
   b->eng = e; b->regex = regex; b->n = n; b->emails = emails; b->captures = captures;
   // resident batches: fewer, larger launches (better SM balance; nothing to overlap with)
   const std::vector<size_t> bounds = chunk_bounds(emails, n, e->chunk_emails * 8, (size_t)3 << 30);
+  std::vector<ThreadCtx> ctxs(e->pool->size());
   cudaStream_t s = e->slots[0].stream;
   int rc = ZKB_OK;
   for (size_t k = 0; k + 1 < bounds.size() && rc == ZKB_OK; k++) {
     Chunk* ch = new Chunk();
     DeviceChunk* d = new DeviceChunk();
     b->chunks.push_back(ch); b->dev.push_back(d);
-    rc = pack_chunk(e, emails, bounds[k], bounds[k + 1] - bounds[k], regex, *ch, e->slots[0].meta);
+    rc = pack_chunk(e, emails, bounds[k], bounds[k + 1] - bounds[k], regex, *ch, e->slots[0].meta, ctxs);
     if (rc) break;
     rc = sync_keytab(e, s);
     if (rc) break;
