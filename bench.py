@@ -420,7 +420,7 @@ def main():
                        "input_memory": "registered (pinned) host memory: raw messages DMA'd as they are; header parsing, preimages, base64 and "
                                        "body canonicalisation on the device (irregular messages fall back to the host front end)" if direct
                                        else "pageable host memory: bodies canonicalised on host threads into pinned staging",
-                       "collective": "none (1 GPU)" if world == 1 else "NCCL all-gather of verdict words per step (inside the timed region)", "rsa_lanes": args.rsa_lanes or 8},
+                       "collective": "none (1 GPU)" if world == 1 else "NCCL all-gather of verdict words per step (inside the timed region)", "rsa_lanes": args.rsa_lanes or 4},
             "roofline": roofline, "roofline_int": roofline_int, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "emails/s", "h2d_bytes_per_step": e2e_bytes["h2d_bytes"],
                     "d2h_bytes_per_step": e2e_bytes["d2h_bytes"], "ms_per_step": 1e3 * e2e_s / K,

@@ -28,7 +28,7 @@ def test_sha256_kernel_vs_hashlib_and_oracle(engine):
         assert g == oracle.sha256(m)
 
 
-@pytest.mark.parametrize("lanes", [4, 8, 16])
+@pytest.mark.parametrize("lanes", [2, 4, 8, 16])
 def test_rsa_kernel_vs_oracle(lanes):
     from cryptography.hazmat.primitives import hashes
     from cryptography.hazmat.primitives.asymmetric import padding

@@ -306,7 +306,7 @@ struct zkb_engine {
   size_t smem_optin = 0;
   int64_t now_unix = 0;
   size_t chunk_emails = 32768;
-  uint32_t rsa_lanes = 8;
+  uint32_t rsa_lanes = 4;   // lanes per 2048-bit signature (measured best on B200: 0.89 of the IMAD.WIDE peak)
   ThreadPool* pool = nullptr;
   BlockPool blocks;
   Slot slots[3];

@@ -11,7 +11,7 @@ static void launch_t(int lanes, const uint32_t* sig_arena, const RsaItem* items,
     rsa_verify_kernel<128, TT, G><<<grid, block, 0, s>>>(sig_arena, items, n, keytab, digests, cand_flags); \
     break;                                                                                                \
   }
-  switch (lanes) { ZKB_RSA_CASE(8) default: ZKB_RSA_CASE(16) }
+  switch (lanes) { ZKB_RSA_CASE(4) ZKB_RSA_CASE(16) default: ZKB_RSA_CASE(8) }
 #undef ZKB_RSA_CASE
 }
 void launch_rsa128(bool generic, int lanes, const uint32_t* sig_arena, const RsaItem* items, uint32_t n,

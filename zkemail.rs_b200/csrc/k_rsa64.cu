@@ -11,7 +11,7 @@ static void launch_t(int lanes, const uint32_t* sig_arena, const RsaItem* items,
     rsa_verify_kernel<64, TT, G><<<grid, block, 0, s>>>(sig_arena, items, n, keytab, digests, cand_flags); \
     break;                                                                                                \
   }
-  switch (lanes) { ZKB_RSA_CASE(4) ZKB_RSA_CASE(16) default: ZKB_RSA_CASE(8) }
+  switch (lanes) { ZKB_RSA_CASE(2) ZKB_RSA_CASE(8) ZKB_RSA_CASE(16) default: ZKB_RSA_CASE(4) }
 #undef ZKB_RSA_CASE
 }
 void launch_rsa64(bool generic, int lanes, const uint32_t* sig_arena, const RsaItem* items, uint32_t n,

@@ -29,8 +29,21 @@ __device__ __constant__ uint32_t SHA_K[64] = {
 __device__ __forceinline__ uint32_t rotr32(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
 
+// 32-bit add issued on the FMA pipe (IMAD: a * one + b, `one` is a run-time 1 the compiler cannot fold).
+// SHA-256 is bound by the ALU pipe (SHF / LOP3 / IADD3, 64 lanes/clk/SM); the FMA pipe is idle, so the
+// additions are moved there and the ALU pipe keeps only the rotates and the boolean functions.
+__device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, uint32_t one) {
+#ifdef ZKB_HOST_EMU
+  return a * one + b;
+#else
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+  return d;
+#endif
+}
+
 // One compression; w[16] holds the big-endian message words and is clobbered.
-__device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) {
+__device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16], uint32_t one) {
   uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll
   for (int i = 0; i < 64; i++) {
@@ -38,14 +51,14 @@ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) 
       uint32_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
       uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
       uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
-      w[i & 15] = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
+      w[i & 15] = fadd(fadd(w[i & 15], s0, one), fadd(w[(i - 7) & 15], s1, one), one);
     }
     uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
     uint32_t ch = (e & f) ^ (~e & g);  // one LOP3
-    uint32_t t1 = h + S1 + ch + SHA_K[i] + w[i & 15];
+    uint32_t t1 = fadd(fadd(fadd(h, S1, one), ch, one), fadd(w[i & 15], SHA_K[i], one), one);
     uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
     uint32_t mj = (a & b) ^ (a & c) ^ (b & c);  // one LOP3
-    h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + S0 + mj;
+    h = g; g = f; f = e; e = fadd(d, t1, one); d = c; c = b; b = a; a = fadd(fadd(t1, S0, one), mj, one);
   }
   st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
@@ -56,7 +69,7 @@ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) 
 __global__ void __launch_bounds__(128)
 sha256_batch_kernel(const uint8_t* __restrict__ arena, const uint64_t* __restrict__ msg_off,
                     const uint32_t* __restrict__ msg_len, const uint32_t* __restrict__ order,
-                    uint32_t n, uint32_t* __restrict__ digests) {
+                    uint32_t n, uint32_t* __restrict__ digests, uint32_t one) {
   uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   uint32_t m = order ? order[idx] : idx;
@@ -89,7 +102,7 @@ sha256_batch_kernel(const uint8_t* __restrict__ arena, const uint64_t* __restric
       }
       if (blk == total - 1) { w[14] = len >> 29; w[15] = len << 3; }
     }
-    sha256_compress(st, w);
+    sha256_compress(st, w, one);
   }
   uint4* o = reinterpret_cast<uint4*>(digests + (size_t)m * 8);
   o[0] = make_uint4(st[0], st[1], st[2], st[3]);
