@@ -26,6 +26,8 @@ def lib():
         L.zg_keys_destroy.argtypes = [C.c_void_p]
         L.zg_raw_bound.restype = C.c_size_t
         L.zg_raw_bound.argtypes = [C.c_size_t]
+        L.zg_compact.restype = C.c_size_t
+        L.zg_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
         L.zg_generate.argtypes = [C.c_void_p, C.c_uint64, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         _lib = L
@@ -88,6 +90,9 @@ class MailPool:
                                self.raw_len.ctypes.data, 1 if token else 0, qp_percent,
                                threads or (os.cpu_count() or 1))
         assert rc == 0, "generator failed"
+        # pack the arena the way a mail spool would be: messages back to back, 64-byte aligned starts
+        used = lib().zg_compact(self.raw.ctypes.data, self.raw_off.ctypes.data, self.raw_len.ctypes.data, n, 64)
+        self.raw = self.raw[: used + 64]
         # the key each email is verified with ("wrong key" negatives get a same-size neighbour)
         self.verify_key = self.key_idx.copy()
         wrong = self.neg_kind == 3

@@ -298,3 +298,16 @@ int zg_generate(void *kp, uint64_t seed, size_t n, const uint32_t *body_len, con
   for (int t = 0; t < n_threads; t++) { pthread_join(th[t], NULL); rc |= args[t].rc; }
   return rc;
 }
+
+/* Packs the generated messages tightly (each start `align`-byte aligned) by moving them towards the front of
+ * `raw`; rewrites raw_off.  Returns the number of bytes in use. */
+size_t zg_compact(uint8_t *raw, uint64_t *raw_off, const uint32_t *raw_len, size_t n, size_t align) {
+  size_t o = 0;
+  for (size_t i = 0; i < n; i++) {
+    o = (o + align - 1) / align * align;
+    if (raw_off[i] != o) memmove(raw + o, raw + raw_off[i], raw_len[i]);
+    raw_off[i] = o;
+    o += raw_len[i];
+  }
+  return o;
+}

@@ -130,7 +130,11 @@ void emu_canon_body(const uint8_t* span, const uint64_t* off, const uint32_t* le
 // Device front end (frontend.cuh: fe_process) against the host front end (dkim_host.hpp) on one message.
 // returns 0 = the device path declines (fallback), 1 = live and identical to the host, 2 = both report a
 // mail parse error, negative = MISMATCH (code tells which field).
-int emu_fe_compare(const uint8_t* raw, uint32_t n, const uint8_t* dom, uint32_t dom_len, uint32_t k, uint32_t limbs) {
+int emu_fe_compare(const uint8_t* raw_in, uint32_t n, const uint8_t* dom, uint32_t dom_len, uint32_t k, uint32_t limbs) {
+  // the device reads whole aligned 16-byte blocks: give it the message at an odd offset inside a padded buffer
+  std::vector<uint8_t> padded((size_t)n + 96, 0x3B);
+  uint8_t* raw = padded.data() + 16 + ((16 - ((uintptr_t)padded.data() & 15)) & 15) + 5;
+  memcpy(raw, raw_in, n);
   std::vector<uint8_t> pre(FE_PRE_CAP + 64, 0xEE);
   std::vector<uint32_t> sigw(limbs, 0xDEADBEEFu);
   FeOut fo;
