@@ -382,7 +382,7 @@ def main():
     roofline = {"kernel": "rsa_verify_kernel" if dom == "rsa" else "sha256_batch_kernel", "bound": "hbm",
                 "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms,
-                "launches_per_step": -(-n_emails // ((args.chunk or 32768) * 8)), "note": "integer-issue bound, not HBM bound: see roofline_int; achieved/traffic are "
+                "launches_per_step": -(-n_emails // ((args.chunk or 65536) * 4)), "note": "integer-issue bound, not HBM bound: see roofline_int; achieved/traffic are "
                 "summed over the launches of one step (one per resident chunk)"}
     roofline_int = {
         "rsa_verify_kernel": {"bound": "fma pipe (IMAD.WIDE)", "achieved": stats["rsa_macs"] / (fam_best["rsa"] * 1e-3) / 1e9 if fam_best["rsa"] > 0 else None,

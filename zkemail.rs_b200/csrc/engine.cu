@@ -305,7 +305,7 @@ struct zkb_engine {
   int device = 0, sm_count = 148;
   size_t smem_optin = 0;
   int64_t now_unix = 0;
-  size_t chunk_emails = 32768;
+  size_t chunk_emails = 65536;   // e2e pipeline chunk (also capped at 256 MB of raw bytes); resident batches use 4x
   uint32_t rsa_lanes = 4;   // lanes per 2048-bit signature (measured best on B200: 0.89 of the IMAD.WIDE peak)
   ThreadPool* pool = nullptr;
   BlockPool blocks;
@@ -1509,7 +1509,7 @@ int zkb_batch_prepare(zkb_engine* e, const zkb_email_view* emails, size_t n, con
   zkb_batch* b = new zkb_batch();
   b->eng = e; b->regex = regex; b->n = n; b->emails = emails; b->captures = captures;
   // resident batches: fewer, larger launches (better SM balance; nothing to overlap with)
-  const std::vector<size_t> bounds = chunk_bounds(emails, n, e->chunk_emails * 8, (size_t)3 << 30);
+  const std::vector<size_t> bounds = chunk_bounds(emails, n, e->chunk_emails * 4, (size_t)3 << 30);
   std::vector<ThreadCtx> ctxs(e->pool->size());
   cudaStream_t s = e->slots[0].stream;
   int rc = ZKB_OK;
