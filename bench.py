@@ -395,6 +395,12 @@ def main():
     for k in ("rsa_verify_kernel", "sha256_batch_kernel"):
         a = roofline_int[k]
         a["frac"] = (a["achieved"] / a["peak"]) if a["achieved"] and a["peak"] else None
+    sh = roofline_int["sha256_batch_kernel"]
+    # 1400 = algorithmic integer instructions per 64-byte block; the kernel issues 1028 of them on the ALU pipe
+    # (SHF/LOP3) and moves the 594 additions to the otherwise idle FMA pipe (IMAD), so the algorithmic rate can
+    # exceed the ALU-pipe peak; alu_pipe_frac is the share of the ALU pipe actually used (ncu: 0.87)
+    sh["alu_pipe_frac"] = sh["frac"] * 1028.0 / 1400.0 if sh["frac"] else None
+    sh["note"] = "frac = algorithmic instr rate / ALU-pipe peak; additions run on the FMA pipe, see alu_pipe_frac"
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu_baseline = None
