@@ -280,3 +280,22 @@ def test_device_front_end_source_on_dirty_mail(headers, body, canon, hnames, ext
     raw += b"\r\n" + body
     r = _fe_compare(raw, b"Example.COM", k=6, limbs=32)
     assert r >= 0, (r, raw)
+
+
+def test_regex_unicode_perl_classes():
+    r"""\d \w \s follow the Unicode definitions in (?u) mode (as DFARegex::new compiles them) and the ASCII
+    ones under (?-u)."""
+    def spans(pat, hay):
+        fwd, bwd = emu.regex_compile(pat.encode())
+        return oracle.dfa_find_iter(fwd, bwd, hay.encode(), 64)[1]
+    def bytespans(pat, hay, flags=0):
+        b = lambda i: len(hay[:i].encode())
+        return [(b(m.start()), b(m.end())) for m in re.finditer(pat, hay, flags)]
+    hay = "id ١٢٣ and 456, héllo wörld_ok\u00a0x\u2003y naïve"
+    assert spans(r"\d+", hay) == bytespans(r"\d+", hay)
+    assert spans(r"\w+", hay) == bytespans(r"\w+", hay)
+    assert spans(r"\s+", hay) == bytespans(r"\s+", hay)
+    assert spans(r"\D+", "12ab٣") == bytespans(r"\D+", "12ab٣")
+    assert spans(r"(?-u:\d+)", hay) == bytespans(r"\d+", hay, re.ASCII)
+    assert spans(r"(?-u:\w+)", "héllo") == [(0, 1), (3, 6)]
+    assert spans(r"[\d_]+", "a_١_9") == bytespans(r"[\d_]+", "a_١_9")

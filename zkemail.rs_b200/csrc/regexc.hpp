@@ -13,7 +13,7 @@
 //
 // Supported syntax: literals, escapes (\n \r \t \f \v \a \xHH \x{H..} \u{H..} \uHHHH and escaped
 // punctuation), `.`, classes with ranges / negation / POSIX names / nested \d \w \s, \d \w \s \D \W \S
-// (ASCII definitions; see DESIGN.md "regex compiler limits"), groups (capturing, non-capturing,
+// (Unicode definitions in (?u) mode from generated tables, ASCII under (?-u)), groups (capturing, non-capturing,
 // named), alternation, greedy and lazy * + ? {m} {m,} {m,n}, anchors ^ $ \A \z, flags i m s U u.
 // Rejected (ZKB_E_REGEX): look-around other than anchors (\b \B), Unicode property classes (\p),
 // class set operations, back-references, the x flag.
@@ -27,6 +27,8 @@
 #include <unordered_map>
 #include <utility>
 #include <vector>
+
+#include "unicode_tables.hpp"
 
 namespace zkb {
 namespace rx {
@@ -82,6 +84,7 @@ struct Parser {
   std::vector<Node> nodes;
   std::string err;
   int depth = 0;
+  bool cur_unicode = true;   // the u flag in effect where an escape is being parsed
 
   Parser(const char* s, size_t len) : p((const uint8_t*)s), n(len) {}
   int add(const Node& nd) { nodes.push_back(nd); return (int)nodes.size() - 1; }
@@ -144,8 +147,23 @@ struct Parser {
     nd.kind = Node::CLASS; nd.ranges = r; nd.unicode = f.u;
     return add(nd);
   }
-  static bool perl_class(uint32_t c, RangeSet& out, bool& neg) {
+  // \d \w \s: Unicode definitions in (?u) mode (regex-syntax: \p{Nd}, \p{Alphabetic}+M+Nd+Pc+Join_Control,
+  // \p{White_Space}; tables generated from Unicode 15.0, see tools/gen_unicode_tables.py), ASCII under (?-u)
+  static bool perl_class(uint32_t c, RangeSet& out, bool& neg, bool unicode) {
     neg = (c == 'D' || c == 'W' || c == 'S');
+    if (unicode) {
+      const uint32_t (*t)[2] = nullptr;
+      size_t n = 0;
+      switch (c | 32) {
+        case 'd': t = UNI_DIGIT; n = UNI_DIGIT_N; break;
+        case 'w': t = UNI_WORD; n = UNI_WORD_N; break;
+        case 's': t = UNI_SPACE; n = UNI_SPACE_N; break;
+        default: return false;
+      }
+      out.clear();
+      for (size_t i = 0; i < n; i++) out.push_back(Range(t[i][0], t[i][1]));
+      return true;
+    }
     switch (c | 32) {
       case 'd': out = {Range('0', '9')}; return true;
       case 'w': out = {Range('0', '9'), Range('A', 'Z'), Range('_', '_'), Range('a', 'z')}; return true;
@@ -193,7 +211,7 @@ struct Parser {
       case 'v': c = 0x0B; return 0;
       case 'a': c = 0x07; return 0;
       case 'x': case 'u': case 'U': return hex_escape(e, c) ? 0 : -1;
-      case 'd': case 'D': case 'w': case 'W': case 's': case 'S': perl_class(e, cls, neg); return 1;
+      case 'd': case 'D': case 'w': case 'W': case 's': case 'S': perl_class(e, cls, neg, cur_unicode); return 1;
       case 'A': if (in_class) break; look = LOOK_START_TEXT; return 2;
       case 'z': if (in_class) break; look = LOOK_END_TEXT; return 2;
       default: break;
@@ -236,6 +254,7 @@ struct Parser {
     return false;
   }
   int parse_class(const Flags& f) {  // at '['
+    cur_unicode = f.u;
     pos++;
     bool negated = false;
     if (pos < n && p[pos] == '^') { negated = true; pos++; }
@@ -398,6 +417,7 @@ struct Parser {
     }
     if (c == '\\') {
       pos++;
+      cur_unicode = f.u;
       uint32_t lit; RangeSet cls; bool neg; int look;
       int k = escape(lit, cls, neg, look, false);
       if (k < 0) return -1;
@@ -666,8 +686,8 @@ struct Determinizer {
     return intern(d);
   }
   // unit: 0..255 byte, 256 = end of input
-  uint32_t next(uint32_t from, int unit) {
-    DState src = states[from];
+  // src must be a copy of states[from] (intern() may grow `states`)
+  uint32_t next(const DState& src, int unit) {
     std::vector<int> cur = src.ids;
     if (src.look_need) {
       int have = src.look_have;
@@ -726,12 +746,59 @@ inline bool determinize(const Nfa& nfa, bool leftmost_first, bool with_unanchore
   for (uint32_t s = 0; s < det.states.size(); s++) {
     if (det.states.size() > 20000) { err = "DFA too large (more than 20000 states)"; return false; }
     std::vector<uint32_t> row(out.n_classes);
-    for (uint32_t c = 0; c < out.n_classes; c++) row[c] = det.next(s, rep[c]);
+    const DState src = det.states[s];
+    for (uint32_t c = 0; c < out.n_classes; c++) row[c] = det.next(src, rep[c]);
     out.trans.push_back(row);
   }
   out.is_match.resize(det.states.size());
   for (size_t s = 0; s < det.states.size(); s++) out.is_match[s] = det.states[s].is_match;
   return true;
+}
+
+// Moore partition refinement: merges states that no input can tell apart (same match flag now and after every
+// byte-class / EOI sequence).  Search results are unchanged: the scan only observes transitions, match flags and
+// the dead state.  States that can no longer reach a match collapse into the dead state, so scans also stop earlier.
+// Smaller tables matter on the device: they stay in shared memory and qualify for 256-wide DIRECT rows.
+inline void minimize(Dfa& d) {
+  const size_t ns = d.trans.size(), nc = d.n_classes;
+  if (ns <= 1) return;
+  std::vector<uint32_t> cls(ns);
+  for (size_t s = 0; s < ns; s++) cls[s] = d.is_match[s] ? 1u : 0u;
+  size_t n_cls = 2;
+  for (;;) {
+    std::map<std::vector<uint32_t>, uint32_t> sig_id;
+    std::vector<uint32_t> next_cls(ns);
+    std::vector<uint32_t> sig(nc + 1);
+    for (size_t s = 0; s < ns; s++) {
+      sig[0] = cls[s];
+      for (size_t c = 0; c < nc; c++) sig[c + 1] = cls[d.trans[s][c]];
+      auto it = sig_id.find(sig);
+      if (it == sig_id.end()) it = sig_id.emplace(sig, (uint32_t)sig_id.size()).first;
+      next_cls[s] = it->second;
+    }
+    const size_t n_new = sig_id.size();
+    cls.swap(next_cls);
+    if (n_new == n_cls) break;
+    n_cls = n_new;
+  }
+  // renumber so that the dead state's block is 0
+  std::vector<uint32_t> remap(n_cls, 0xFFFFFFFFu);
+  uint32_t next_id = 0;
+  remap[cls[0]] = next_id++;
+  for (size_t s = 0; s < ns; s++) if (remap[cls[s]] == 0xFFFFFFFFu) remap[cls[s]] = next_id++;
+  std::vector<std::vector<uint32_t>> trans(n_cls, std::vector<uint32_t>(nc, 0));
+  std::vector<bool> is_match(n_cls, false);
+  std::vector<bool> done(n_cls, false);
+  for (size_t s = 0; s < ns; s++) {
+    const uint32_t b = remap[cls[s]];
+    if (done[b]) continue;
+    done[b] = true;
+    is_match[b] = d.is_match[s];
+    for (size_t c = 0; c < nc; c++) trans[b][c] = remap[cls[d.trans[s][c]]];
+  }
+  for (int i = 0; i < 12; i++) d.start[i] = remap[cls[d.start[i]]];
+  d.trans.swap(trans);
+  d.is_match.swap(is_match);
 }
 
 // ZDF1 serialisation: dead state 0, then match states as one contiguous id range, then the rest.
@@ -779,6 +846,7 @@ inline bool compile(const char* pattern, size_t len, std::vector<uint8_t>& fwd, 
     if (nfa.overflow) { err = "pattern too large (NFA state limit)"; return false; }
     Dfa d;
     if (!determinize(nfa, rev == 0, rev == 0, d, err)) return false;
+    minimize(d);
     emit_zdf(d, base_flags | (rev ? 1u : 0u), rev ? bwd : fwd);
   }
   return true;
