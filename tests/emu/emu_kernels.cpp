@@ -104,6 +104,7 @@ int emu_dfa_scan(const uint8_t* fwd, size_t fl, const uint8_t* bwd, size_t bl, c
   std::vector<DfaItem> items(n);
   for (uint32_t i = 0; i < n; i++) { items[i].hay_off = off[i]; items[i].msg = i; items[i].out_slot = i; }
   const unsigned block = 128;
+  if (fb.size() + rb.size() > 200000) use_smem = 0;   // as the launchers do: tables that do not fit stay in global memory
   emu::launch((n + block - 1) / block, block, [&]() {
 #define RUN1(TT, D, S) dfa_scan_kernel<TT, D, S>(arena, items.data(), n, len, fb.data(), (uint32_t)fb.size(), rb.data(), (uint32_t)rb.size(), qp, (uint4*)out)
 #define RUN(TT, D) do { if (use_smem) RUN1(TT, D, true); else RUN1(TT, D, false); } while (0)
