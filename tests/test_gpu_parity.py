@@ -69,7 +69,7 @@ def test_rsa_kernel_vs_oracle(lanes):
 
 PATTERNS = [r"abc", r"a+", r"a*", r"(a|ab)(c|bcd)", r"from:[^\r\n]*@example\.com", r"subject:[^\r\n]+",
             r"Transaction ID: [A-Z0-9]+", r"(?i)hello", r"a{2,4}", r"^abc", r"abc$", r"(?m)^a+$", r".*",
-            r"[^a]+", r"(foo|foobar|fo)", r"\d+\.\d+", r"to:[^\r\n]+\r\n"]
+            r"[^a]+", r"(foo|foobar|fo)", r"\d+\.\d+", r"to:[^\r\n]+\r\n", r"\w+@\w+\.com"]
 
 
 @pytest.mark.parametrize("qp", [False, True])
