@@ -121,58 +121,65 @@ struct Searcher {
 
   // find_fwd: unanchored leftmost-first from `from` (prev = cleaned byte before it, -1 at text
   // start).  On a match: end = position of the match end, end_byte = byte there (-1 for EOI).
-  __device__ bool fwd(Cur from, int prev, Cur& end, int& end_byte) {
+  //
+  // The scan walks aligned 16-byte blocks held in registers (one LDG.128 per 16 bytes per lane) and is
+  // branch-free inside a block: bytes before the start offset / past the end, and the bytes of "=\r\n" soft
+  // breaks (QP), are predicated off instead of taking a slower path, so every lane of a warp executes the same
+  // instruction stream whatever its data looks like (a lane that branches on a per-byte event leaves the
+  // convergent group; a lane that falls back to a byte-wise path makes its whole warp wait).  The dead state
+  // is absorbing (row 0 is all zeros) and never a match, so finishing the block after dying is harmless.
+  template <bool QP>
+  __device__ bool fwd_impl(Cur from, int prev, Cur& end, int& end_byte) {
     if (from.c > n) return false;
     uint32_t sid = f.start(false, prev < 0 ? 2u : f.smap[prev]);
     if (sid == 0) return false;
     bool have = false;
-    Cur p = from;
-    // Single-exit loop (no return inside) so that the lanes of a warp reconverge every iteration.
-    while (p.c < n && sid != 0) {
-      bool block = (p.o & 15u) == 0 && p.o + 16 <= n;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (block) {
-        // a whole 16-byte block from registers (one LDG.128 per 16 bytes per lane).  With soft-break
-        // removal on, blocks containing '=' take the byte-wise path below.
-        v = __ldg(reinterpret_cast<const uint4*>(h + p.o));
-        if (qp) {
-          const uint32_t e = 0x3d3d3d3du;
-          const uint32_t x0 = v.x ^ e, x1 = v.y ^ e, x2 = v.z ^ e, x3 = v.w ^ e;
-          const uint32_t z = ((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | ((x2 - 0x01010101u) & ~x2) | ((x3 - 0x01010101u) & ~x3);
-          block = (z & 0x80808080u) == 0;
-        }
-      }
-      if (block) {
-        // Branch-free over the block: lanes must not split on per-byte events.  The dead state is
-        // absorbing (row 0 is all zeros) and never a match, so finishing the block after dying is
-        // harmless; the last match position inside the block is kept in mk.
-        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-        int mk = -1;
+    uint32_t c = from.c, o = from.o, skip = 0;
+    const uint4* hb = reinterpret_cast<const uint4*>(h);
+    while (o < n && sid != 0) {
+      const uint32_t base = o & ~15u;
+      const uint32_t kend = (n - base) < 16u ? (n - base) : 16u;
+      const uint32_t mask = ((1u << kend) - 1u) & ~((1u << (o & 15u)) - 1u);   // bytes of this block to consume
+      const uint4 v = __ldg(hb + (base >> 4));
+      uint32_t w5[5] = {v.x, v.y, v.z, v.w, 0u};
+      if (QP && base + 16 < n) w5[4] = __ldg(reinterpret_cast<const uint32_t*>(h + base + 16));  // look-ahead for k = 14, 15
+      int mk = -1;
+      uint32_t mc = 0, mb = 0;
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-          const uint32_t b = (w4[k >> 2] >> ((k & 3) * 8)) & 0xffu;
-          sid = f.next(sid, b);
-          mk = (sid >= f.min_m && sid <= f.max_m) ? k : mk;
+      for (int k = 0; k < 16; k++) {
+        const uint32_t b = (w5[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+        bool act = (mask >> k) & 1u;
+        if (QP) {
+          const uint32_t b1 = (w5[(k + 1) >> 2] >> (((k + 1) & 3) * 8)) & 0xffu;
+          const uint32_t b2 = (w5[(k + 2) >> 2] >> (((k + 2) & 3) * 8)) & 0xffu;
+          const bool sb = act && skip == 0 && b == '=' && b1 == '\r' && b2 == '\n' && base + k + 2 < n;
+          const bool drop = act && (skip != 0 || sb);
+          skip = sb ? 2u : ((act && skip != 0) ? skip - 1u : skip);
+          act = act && !drop;
         }
-        if (mk >= 0) {
-          have = true; end.c = p.c + (uint32_t)mk; end.o = p.o + (uint32_t)mk;
-          const uint32_t w = (mk & 8) ? ((mk & 4) ? v.w : v.z) : ((mk & 4) ? v.y : v.x);
-          end_byte = (int)((w >> ((mk & 3) * 8)) & 0xffu);
-        }
-        p.c += 16; p.o += 16;
-        skip_soft(p.o);
-        if (p.o >= n) clen = p.c;
-      } else {
-        Cur at = p;
-        uint32_t b = take(p);
-        sid = f.next(sid, b);
-        if (sid >= f.min_m && sid <= f.max_m) { have = true; end = at; end_byte = (int)b; }
+        const uint32_t ns = f.next(sid, b);
+        sid = act ? ns : sid;
+        const bool m = act && sid >= f.min_m && sid <= f.max_m;
+        mk = m ? k : mk; mc = m ? c : mc; mb = m ? b : mb;
+        c += act ? 1u : 0u;
       }
+      if (mk >= 0) { have = true; end.c = mc; end.o = base + (uint32_t)mk; end_byte = (int)mb; }
+      o = base + 16u;
+    }
+    if (from.o < n && o >= n) clen = c;   // crossed the end of the real bytes: the cleaned length is known
+    // virtual zero padding up to the original length (only bodies that had soft breaks get here with c < n)
+    while (c < n && sid != 0 && o >= n) {
+      sid = f.next(sid, 0u);
+      if (sid >= f.min_m && sid <= f.max_m) { have = true; end.c = c; end.o = n; end_byte = 0; }
+      c++;
     }
     if (sid == 0) return have;  // dead: the search ends with the last recorded match
     sid = f.next_eoi(sid);
-    if (f.is_match(sid)) { have = true; end = p; end_byte = -1; }
+    if (f.is_match(sid)) { have = true; end.c = n; end.o = n; end_byte = -1; }
     return have;
+  }
+  __device__ __forceinline__ bool fwd(Cur from, int prev, Cur& end, int& end_byte) {
+    return qp ? fwd_impl<true>(from, prev, end, end_byte) : fwd_impl<false>(from, prev, end, end_byte);
   }
   // find_rev: anchored, over cleaned [from.c, end.c); ms = leftmost start of a match ending at end
   __device__ bool rev(Cur from, int prev_of_from, Cur end, int end_byte, uint32_t& ms) {
