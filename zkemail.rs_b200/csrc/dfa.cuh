@@ -139,31 +139,50 @@ struct Searcher {
     while (o < n && sid != 0) {
       const uint32_t base = o & ~15u;
       const uint32_t kend = (n - base) < 16u ? (n - base) : 16u;
-      const uint32_t mask = ((1u << kend) - 1u) & ~((1u << (o & 15u)) - 1u);   // bytes of this block to consume
+      const uint32_t mask = ((1u << kend) - 1u) & ~((1u << (o & 15u)) - 1u);   // bytes of this block in range
       const uint4 v = __ldg(hb + (base >> 4));
-      uint32_t w5[5] = {v.x, v.y, v.z, v.w, 0u};
-      if (QP && base + 16 < n) w5[4] = __ldg(reinterpret_cast<const uint32_t*>(h + base + 16));  // look-ahead for k = 14, 15
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+      // bytes to drop: the tail of a soft break that started in the previous block, plus every "=\r\n"
+      // starting in this one.  Only blocks that contain '=' pay for the search (a short, rarely taken branch;
+      // the 16-step transition loop below is common to all lanes).
+      uint32_t drop = skip;
+      if (QP) {
+        const uint32_t e = 0x3d3d3d3du;
+        const uint32_t x0 = v.x ^ e, x1 = v.y ^ e, x2 = v.z ^ e, x3 = v.w ^ e;
+        const uint32_t z = ((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | ((x2 - 0x01010101u) & ~x2) | ((x3 - 0x01010101u) & ~x3);
+        if (z & 0x80808080u) {
+          uint32_t la = 0;   // the two bytes after the block (look-ahead for k = 14, 15)
+          if (base + 16 < n) la = __ldg(reinterpret_cast<const uint32_t*>(h + base + 16));
+          const uint32_t w5[5] = {v.x, v.y, v.z, v.w, la};
+#pragma unroll
+          for (int k = 0; k < 16; k++) {
+            const uint32_t b0 = (w5[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+            const uint32_t b1 = (w5[(k + 1) >> 2] >> (((k + 1) & 3) * 8)) & 0xffu;
+            const uint32_t b2 = (w5[(k + 2) >> 2] >> (((k + 2) & 3) * 8)) & 0xffu;
+            const bool sb = b0 == '=' && b1 == '\r' && b2 == '\n' && base + k + 2 < n && ((mask >> k) & 1u);
+            drop |= sb ? (7u << k) : 0u;
+          }
+        }
+      }
+      skip = drop >> 16;                          // a soft break at k = 14 / 15 spills into the next block
+      const uint32_t cons = mask & ~drop;         // bytes the DFA consumes
       int mk = -1;
-      uint32_t mc = 0, mb = 0;
 #pragma unroll
       for (int k = 0; k < 16; k++) {
-        const uint32_t b = (w5[k >> 2] >> ((k & 3) * 8)) & 0xffu;
-        bool act = (mask >> k) & 1u;
-        if (QP) {
-          const uint32_t b1 = (w5[(k + 1) >> 2] >> (((k + 1) & 3) * 8)) & 0xffu;
-          const uint32_t b2 = (w5[(k + 2) >> 2] >> (((k + 2) & 3) * 8)) & 0xffu;
-          const bool sb = act && skip == 0 && b == '=' && b1 == '\r' && b2 == '\n' && base + k + 2 < n;
-          const bool drop = act && (skip != 0 || sb);
-          skip = sb ? 2u : ((act && skip != 0) ? skip - 1u : skip);
-          act = act && !drop;
-        }
+        const uint32_t b = (w4[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+        const bool act = (cons >> k) & 1u;
         const uint32_t ns = f.next(sid, b);
         sid = act ? ns : sid;
-        const bool m = act && sid >= f.min_m && sid <= f.max_m;
-        mk = m ? k : mk; mc = m ? c : mc; mb = m ? b : mb;
-        c += act ? 1u : 0u;
+        mk = (act && sid >= f.min_m && sid <= f.max_m) ? k : mk;
       }
-      if (mk >= 0) { have = true; end.c = mc; end.o = base + (uint32_t)mk; end_byte = (int)mb; }
+      if (mk >= 0) {
+        have = true;
+        end.c = c + (uint32_t)__popc(cons & ((1u << mk) - 1u));
+        end.o = base + (uint32_t)mk;
+        const uint32_t w = (mk & 8) ? ((mk & 4) ? v.w : v.z) : ((mk & 4) ? v.y : v.x);
+        end_byte = (int)((w >> ((mk & 3) * 8)) & 0xffu);
+      }
+      c += (uint32_t)__popc(cons);
       o = base + 16u;
     }
     if (from.o < n && o >= n) clen = c;   // crossed the end of the real bytes: the cleaned length is known
