@@ -43,6 +43,42 @@ def _worker(rank, world, port, n, q):
     dist.destroy_process_group()
 
 
+def _worker_api(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from zkemail_rs_b200 import shard
+    from zkemail_rs_b200.engine import RESULT_DTYPE
+
+    class StubEngine:   # stands in for the per-rank CUDA engine: the record content encodes the email
+        def verify_batch(self, emails):
+            out = np.zeros(len(emails), dtype=RESULT_DTYPE)
+            for i, e in enumerate(emails):
+                out["status"][i] = 0 if e % 5 else 3
+                out["header_hash"][i, 0] = e % 251
+            return out
+    emails = list(range(n))
+    full = shard.verify_batch_sharded(StubEngine(), emails)
+    ok = (len(full) == n and all(int(full["status"][i]) == (0 if i % 5 else 3) for i in range(n))
+          and all(int(full["header_hash"][i, 0]) == i % 251 for i in range(n)))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_verify_batch_sharded_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_api, args=(r, 2, port, 777, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
 @pytest.mark.parametrize("n", [1001, 2])
 def test_shard_and_allgather_world2(n):
     ctx = mp.get_context("spawn")

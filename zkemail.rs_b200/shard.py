@@ -54,3 +54,19 @@ def all_gather_records(local: np.ndarray, n_total: int, rank: int, world: int, d
     dist.all_gather(outs, t)
     parts = [o.cpu().numpy()[: sizes[r]] for r, o in enumerate(outs)]
     return np.concatenate(parts, axis=0).reshape(-1).view(local.dtype)
+
+
+def verify_batch_sharded(engine, emails, regex_info=None, device=None):
+    """verify_email over a batch sharded by email across the ranks of the default process group: every
+    rank verifies its contiguous range on its own GPU (engine = this rank's Engine) and one all-gather of
+    the fixed-size result records gives every rank the records of the whole batch, in email order.
+    Works with one process (no process group) as a plain batch call."""
+    import torch.distributed as dist
+    n = len(emails)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return engine.verify_with_regex_batch(emails, regex_info) if regex_info is not None else engine.verify_batch(emails)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    lo, hi = shard_range(n, rank, world)
+    mine = emails[lo:hi]
+    local = engine.verify_with_regex_batch(mine, regex_info) if regex_info is not None else engine.verify_batch(mine)
+    return all_gather_records(local, n, rank, world, device=device)
