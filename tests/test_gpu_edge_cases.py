@@ -11,7 +11,7 @@ import oracle
 import zkemail_rs_b200 as z
 from zkemail_rs_b200 import synth
 from zkemail_rs_b200.structs import RegexInfo, RegexPattern, CompiledRegex
-from tests.util import NOW, assert_records_equal, key_pool
+from tests.util import NOW, assert_records_equal, key_pool, mixed_emails
 
 pytestmark = pytest.mark.gpu
 
@@ -240,3 +240,26 @@ def test_status_codes_registered_memory(engine):
     for i, (g, e) in enumerate(zip(got, exp)):
         assert_records_equal(g, e, i)
     assert [int(g["status"]) for g in got][:5] == [0, 1, 1, 2, 9]
+
+
+def test_front_end_paths_agree(engine, monkeypatch):
+    """One mixed batch through the three input paths — staged device front end (pageable views, the default),
+    host front end (ZKB_NO_DEVICE_FRONTEND) and registered memory — gives identical records, equal to the oracle's."""
+    from tests.util import contiguous_views
+    emails, _ = mixed_emails(seed=17, n_pos=48)
+    exp = oracle.verify_batch(emails, now=NOW)
+    staged = engine.verify_batch(emails)
+    assert engine.last_batch_bytes()["h2d_bytes"] > sum(len(e.raw_email) for e in emails)   # raw messages travelled
+    monkeypatch.setenv("ZKB_NO_DEVICE_FRONTEND", "1")
+    host = engine.verify_batch(emails)
+    monkeypatch.delenv("ZKB_NO_DEVICE_FRONTEND")
+    buf, views = contiguous_views(emails)
+    engine.register_host(buf)
+    try:
+        reg = engine.verify_views(views)
+    finally:
+        engine.unregister_host(buf)
+    for i, e in enumerate(exp):
+        assert_records_equal(staged[i], e, i)
+        assert_records_equal(host[i], e, i)
+        assert_records_equal(reg[i], e, i)

@@ -206,6 +206,7 @@ struct CandRec {        // one DKIM-Signature header that reaches the cryptograp
   int32_t key_id;
   uint8_t bh_valid, sig_state, algo, haystack_only;
   uint8_t rsa_list;            // which of the 6 RSA launch lists (valid when the candidate goes to the device)
+  uint32_t raw_blk, raw_local; // staged device front end: where the host copied the raw message (staging block, offset)
 };
 enum { STEP_ERR = 0, STEP_CAND = 1, STEP_SHA1 = 2 };
 struct StepRec { uint32_t cand; uint8_t kind, detail; };
@@ -244,6 +245,7 @@ struct ThreadRecs {
 
 struct DeviceChunk {   // everything one chunk needs in HBM
   DevBuf arena, meta, out, span;   // span: raw message bytes DMA'd from registered host memory (direct mode)
+  const uint8_t* raw_base = nullptr;   // what raw offsets are relative to: span (direct mode) or the arena (staged raw messages)
   const CanonItem* canon_items = nullptr; uint32_t n_canon = 0;
   uint32_t* msg_len_rw = nullptr;
   const FeIn* fe_in = nullptr; FeOut* fe_out = nullptr; uint32_t n_fe = 0;   // device front end
@@ -277,6 +279,7 @@ struct Chunk {  // host view of one chunk
   uint32_t n_canon = 0;
   // device front end (frontend.cuh): headers parsed / preimages built / base64 decoded on the device too
   bool fe = false;
+  bool staged = false;   // fe without direct: the host copies each raw message into the staging blocks (pageable callers)
   size_t o_fein = 0;
   const zkb_email_view* views = nullptr;   // the caller's views of this chunk (borrowed for the call)
   size_t upload_bytes = 0;                 // leading part of the meta buffer that is copied host -> device
@@ -357,6 +360,7 @@ struct ThreadCtx {
   std::unordered_map<int32_t, uint32_t> key_msgs;
   bool oom = false;
   bool direct = false;                 // bodies are canonicalised on the device from the raw span
+  bool staged = false;                 // device front end over raw messages the host copies into the staging blocks
   const uint8_t* span_host = nullptr;
 
   // a device-only arena slot for a body the canon kernel will write (no host bytes)
@@ -414,6 +418,29 @@ struct ThreadCtx {
     return commit(blk, local, len);
   }
 };
+
+// Copy of one raw message into pinned staging (dst 64-byte aligned, capacity rounded up to 64).  Streaming
+// stores: the destination is read next by the DMA engine, not by a core, so it should not displace the cache
+// or cost a read-for-ownership.  Callers fence once per pack pass (stage_fence).
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) inline void stage_copy_avx2(uint8_t* dst, const uint8_t* src, size_t n) {
+  size_t i = 0;
+  for (; i + 64 <= n; i += 64) {
+    const __m256i a = _mm256_loadu_si256((const __m256i*)(src + i));
+    const __m256i b = _mm256_loadu_si256((const __m256i*)(src + i + 32));
+    _mm256_stream_si256((__m256i*)(dst + i), a);
+    _mm256_stream_si256((__m256i*)(dst + i + 32), b);
+  }
+  if (i < n) memcpy(dst + i, src + i, n - i);
+}
+inline void stage_copy(uint8_t* dst, const uint8_t* src, size_t n) {
+  if (n >= 256 && cpu_has_avx2()) stage_copy_avx2(dst, src, n); else if (n) memcpy(dst, src, n);
+}
+inline void stage_fence() { _mm_sfence(); }
+#else
+inline void stage_copy(uint8_t* dst, const uint8_t* src, size_t n) { if (n) memcpy(dst, src, n); }
+inline void stage_fence() {}
+#endif
 
 int32_t lookup_key(ThreadCtx& c, const uint8_t* der, size_t len, KeyMeta& meta) {
   ThreadCtx::PtrKey& pk = c.ptr_cache[ThreadCtx::ptr_slot(der)];
@@ -638,6 +665,13 @@ void process_email_fe(ThreadCtx& c, const zkb_email_view& em, uint32_t local_idx
   CandRec cd;
   memset(&cd, 0, sizeof cd);
   cd.key_id = key_id; cd.algo = 1; cd.sig_state = SIG_OK; cd.rsa_list = (uint8_t)rsa_list_of(km);
+  if (c.staged) {  // the only host touch of the message bytes: one copy into pinned memory (64-byte aligned, 16+ bytes of slack)
+    const size_t need = ((em.raw_email_len + 16 + 63) >> 6) << 6;
+    uint8_t* p = c.reserve(need, cd.raw_blk, cd.raw_local);
+    if (!p) return;
+    stage_copy(p, em.raw_email, em.raw_email_len);
+    c.tr->blocks[cd.raw_blk].used = cd.raw_local + need;
+  }
   auto virt_msg = [&](size_t cap_len, uint32_t est_len) {
     MsgRec m;
     m.goff = 0; m.len = est_len; m.blk = VIRT_BLK; m.local = (uint32_t)c.tr->virt_used; m.canon = 0;
@@ -702,14 +736,19 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
       }
     }
   }
-  ch.fe = ch.direct && allow_fe && !getenv("ZKB_NO_DEVICE_FRONTEND");
+  ch.fe = allow_fe && !getenv("ZKB_NO_DEVICE_FRONTEND");
+  if (ch.fe && !ch.direct) {  // staged: arena offsets of the staged domains are 32-bit, so keep giant messages on the host path
+    if (getenv("ZKB_NO_STAGED_FRONTEND")) ch.fe = false;
+    for (size_t i = 0; i < ne && ch.fe; i++) if (emails[e0 + i].raw_email_len > ((size_t)64 << 20)) ch.fe = false;
+  }
+  ch.staged = ch.fe && !ch.direct;
   g_prof_prelude += now_s2() - tp0;
   const size_t grain = std::max<size_t>(16, std::min<size_t>(512, ne / (size_t)(T * 8) + 1));
   e->pool->run([&](int tid) {
     const double tb0 = now_s2();
     ThreadCtx& c = ctxs[tid];
     c.eng = e; c.tr = &ch.tr[tid];
-    c.direct = ch.direct; c.span_host = ch.span_host;
+    c.direct = ch.direct; c.span_host = ch.span_host; c.staged = ch.staged;
     c.oom = false;
     c.dom_msgs.clear(); c.key_msgs.clear();          // message indices are per chunk
     for (auto& dslot : c.dom_cache) dslot.p = nullptr;
@@ -723,6 +762,7 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
         if (c.oom) { oom = 1; return; }
       }
     }
+    if (ch.staged) stage_fence();
     g_prof_busy_ns.fetch_add((uint64_t)((now_s2() - tb0) * 1e9));
   });
   if (oom) return ZKB_E_NOMEM;
@@ -830,7 +870,7 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
         const KeyMeta& km = e->key_meta[cd.key_id];
         FeIn fi;
         memset(&fi, 0, sizeof fi);
-        fi.raw_off = (uint64_t)(em.raw_email - ch.span_host);
+        fi.raw_off = ch.staged ? t.blocks[cd.raw_blk].dev_off + cd.raw_local : (uint64_t)(em.raw_email - ch.span_host);
         fi.raw_len = (uint32_t)em.raw_email_len;
         fi.dom_off = (uint32_t)t.msgs[er.dom_msg].goff;   // staged domains sit at the front of the arena (< 4 GiB)
         fi.dom_len = (uint32_t)em.from_domain_len;
@@ -896,10 +936,15 @@ int upload_chunk(zkb_engine* e, Chunk& ch, const zkb_regex_set* rs, DeviceChunk&
     for (auto& b : t.blocks)
       if (b.used) CK(cudaMemcpyAsync(d.arena.p + b.dev_off, b.p, b.used, cudaMemcpyHostToDevice, stream));
   CK(cudaMemcpyAsync(d.meta.p, pin_meta.p, ch.upload_bytes, cudaMemcpyHostToDevice, stream));
-  d.n_canon = 0; d.n_fe = 0;
+  d.n_canon = 0; d.n_fe = 0; d.raw_base = nullptr;
   if (ch.direct && ch.n_canon) {
     if (!d.span.ensure(ch.span_bytes + 256)) return ZKB_E_NOMEM;
     CK(cudaMemcpyAsync(d.span.p, ch.span_host, ch.span_bytes, cudaMemcpyHostToDevice, stream));  // DMA from registered memory
+    d.raw_base = d.span.p;
+  } else if (ch.staged) {
+    d.raw_base = d.arena.p;   // raw messages travelled inside the staging blocks
+  }
+  if (d.raw_base && ch.n_canon) {
     d.canon_items = (const CanonItem*)(d.meta.p + ch.o_canon);
     d.n_canon = ch.n_canon;
   }
@@ -954,10 +999,10 @@ int sync_keytab(zkb_engine* e, cudaStream_t stream) {
 int launch_chunk(zkb_engine* e, const DeviceChunk& d, const zkb_regex_set* rs, cudaStream_t s, cudaEvent_t* ev, uint64_t* launches) {
   uint64_t nl = 0;
   if (d.n_fe) {
-    launch_frontend(d.span.p, d.fe_in, d.n_fe, d.arena.p, d.msg_off, d.msg_len_rw, d.sig_rw, d.cand_bh_rw, d.canon_rw, d.fe_out, s);
+    launch_frontend(d.raw_base, d.fe_in, d.n_fe, d.arena.p, d.msg_off, d.msg_len_rw, d.sig_rw, d.cand_bh_rw, d.canon_rw, d.fe_out, s);
     nl++;
   }
-  if (d.n_canon) { launch_canon_body(d.span.p, d.canon_items, d.n_canon, d.arena.p, d.msg_off, d.msg_len_rw, s); nl++; }
+  if (d.n_canon) { launch_canon_body(d.raw_base, d.canon_items, d.n_canon, d.arena.p, d.msg_off, d.msg_len_rw, s); nl++; }
   if (ev) CK(cudaEventRecord(ev[0], s));
   if (d.M) { launch_sha256(d.arena.p, d.msg_off, d.msg_len, d.order, d.M, d.digests, s); nl++; }
   if (ev) CK(cudaEventRecord(ev[1], s));
@@ -1441,11 +1486,16 @@ static int verify_batch_impl(zkb_engine* e, const zkb_email_view* emails, size_t
     CK(cudaEventRecord(s.done, s.stream));
     busy[si] = true;
     t_upload += now_s() - t1;
-    // resolve the previous chunk while this one is in flight
-    if (k >= 1) {
-      int pj = (int)((k - 1) % 3);
+    // resolve the chunk launched two iterations ago: two chunks stay in flight (one in H2D, one in kernels)
+    // while the host packs the next, so the host only waits when the device is the slower side
+    if (k >= 2) {
+      int pj = (int)((k - 2) % 3);
       if (busy[pj]) rc = finish(pj);
     }
+  }
+  for (size_t k = nchunks >= 2 ? nchunks - 2 : 0; k < nchunks; k++) {  // drain in launch order
+    int si = (int)(k % 3);
+    if (busy[si]) { int r2 = finish(si); if (rc == ZKB_OK) rc = r2; }
   }
   for (int si = 0; si < 3; si++) {
     if (busy[si]) { int r2 = finish(si); if (rc == ZKB_OK) rc = r2; }
