@@ -198,6 +198,33 @@ int zkb_host_canonicalize(const uint8_t *raw_email, size_t raw_email_len, int64_
                           uint8_t **hdr, size_t *hdr_len, uint8_t **body, size_t *body_len,
                           int *detail);
 
+/* ---- host-only: Solidity-ABI packing of the verifier outputs (core/src/io.rs:5-53 VerificationOutput::abi_encode,
+ * helpers/src/io.rs:12-31 AbiDecodable; the step right after the hot path for on-chain consumers) ---- */
+typedef struct zkb_str { const char *s; size_t len; } zkb_str;
+typedef struct zkb_span { uint64_t off, len; } zkb_span;
+/* One output to encode.  with_regex = 0: VerificationOutput::EmailOnly (SolEmailOutput, core/src/io.rs:6-10);
+ * 1: VerificationOutput::WithRegex (SolEmailWithRegexOutput, core/src/io.rs:12-15).  external_inputs is the flattened
+ * [name1, value1, ...] list of EmailVerifierOutput (core/src/circuits.rs:18-27). */
+typedef struct zkb_output_view {
+  const uint8_t *from_domain_hash;  /* 32 bytes */
+  const uint8_t *public_key_hash;   /* 32 bytes */
+  const zkb_str *external_inputs; size_t n_external_inputs;
+  const zkb_str *matches; size_t n_matches;
+  int with_regex;
+} zkb_output_view;
+typedef struct zkb_abi_decoded {
+  int32_t with_regex;
+  uint8_t from_domain_hash[32], public_key_hash[32];
+  uint32_t n_external_inputs, n_matches;
+} zkb_abi_decoded;
+/* Encodes n outputs into one malloc'ed blob (free with zkb_free); output i occupies
+ * [offsets[i], offsets[i+1]) — offsets has n+1 entries, caller-allocated.  threads <= 0: all host cores. */
+int zkb_abi_encode_batch(const zkb_output_view *outs, size_t n, int threads, uint8_t **blob, uint64_t *offsets);
+/* Decodes one blob the way AbiDecodable::abi_decode does (EmailOnly first, then WithRegex; the bytes must be the
+ * canonical encoding).  *spans (malloc'ed, free with zkb_free) locates the n_external_inputs + n_matches strings
+ * inside `data`.  Returns ZKB_E_INVALID where the reference returns Err. */
+int zkb_abi_decode(const uint8_t *data, size_t len, zkb_abi_decoded *out, zkb_span **spans);
+
 /* ---- kernel-level entry points (host buffers in, host buffers out) for parity tests ---- */
 /* SHA-256 of n messages data[off[i] .. off[i]+len[i]) ; out = n x 32 bytes. */
 int zkb_sha256_batch(zkb_engine *e, const uint8_t *data, size_t data_len, const uint64_t *off,

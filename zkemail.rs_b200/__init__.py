@@ -8,3 +8,4 @@ from .engine import (  # noqa: F401,E402
     Engine, EngineUnavailable, RegexError, RegexSet, VerificationPanic, compile_regex,
     canonicalize_signed_email, compile_regex_parts, verify_email, verify_email_with_regex,
 )
+from .io import AbiDecodeError, VerificationOutput, abi_decode, abi_encode_batch  # noqa: F401,E402

@@ -144,6 +144,7 @@ EXPORTED_SYMBOLS = (
     "zkb_regex_compile", "zkb_free", "zkb_sha256_batch", "zkb_rsa_verify_batch",
     "zkb_dfa_scan_batch", "zkb_int_pipe_peaks", "zkb_host_canonicalize", "zkb_batch_device_flags",
     "zkb_host_register", "zkb_host_unregister", "zkb_engine_last_batch_bytes",
+    "zkb_abi_encode_batch", "zkb_abi_decode",
 )
 
 _lib = None
