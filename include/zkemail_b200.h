@@ -198,6 +198,14 @@ int zkb_host_canonicalize(const uint8_t *raw_email, size_t raw_email_len, int64_
                           uint8_t **hdr, size_t *hdr_len, uint8_t **body, size_t *body_len,
                           int *detail);
 
+/* ---- host-only utility for the input generator (helpers/src/generator.rs:16-31): the DKIM-Signature headers of a
+ * message, top to bottom, as generate_email_inputs walks them.  *out (malloc'ed, free with zkb_free) holds *n_sigs
+ * records { u32 valid; u32 d_len; u32 s_len; d bytes; s bytes } back to back (little-endian, unpadded); valid = 1
+ * when cfdkim::validate_header accepts the header (d / s are its d= and s= tag values, FWS removed), else 0 with
+ * empty strings.  Returns ZKB_E_INVALID when mailparse::parse_mail would fail. */
+int zkb_host_dkim_signatures(const uint8_t *raw_email, size_t raw_email_len, int64_t now_unix,
+                             uint8_t **out, size_t *out_len, size_t *n_sigs);
+
 /* ---- host-only: Solidity-ABI packing of the verifier outputs (core/src/io.rs:5-53 VerificationOutput::abi_encode,
  * helpers/src/io.rs:12-31 AbiDecodable; the step right after the hot path for on-chain consumers) ---- */
 typedef struct zkb_str { const char *s; size_t len; } zkb_str;

@@ -5,6 +5,7 @@
 #include <thread>
 #include <vector>
 #include "abi_pack.hpp"
+#include "dkim_host.hpp"
 
 extern "C" {
 
@@ -53,6 +54,35 @@ int zkb_abi_decode(const uint8_t* data, size_t len, zkb_abi_decoded* out, zkb_sp
   if (!q) return ZKB_E_NOMEM;
   std::copy(sp.begin(), sp.end(), q);
   *spans = q;
+  return ZKB_OK;
+}
+
+// helpers/src/generator.rs:16-31: get_all_headers("DKIM-Signature") then validate_header on each, in message order
+int zkb_host_dkim_signatures(const uint8_t* raw, size_t n, int64_t now_unix, uint8_t** out, size_t* out_len, size_t* n_sigs) {
+  using namespace zkb;
+  if ((!raw && n) || !out || !out_len || !n_sigs) return ZKB_E_INVALID;
+  *out = nullptr; *out_len = 0; *n_sigs = 0;
+  std::vector<HeaderField> hs;
+  size_t body_off = 0;
+  if (!parse_headers(raw, n, hs, body_off)) return ZKB_E_INVALID;
+  std::vector<uint8_t> buf;
+  auto put32 = [&](uint32_t v) { for (int i = 0; i < 4; i++) buf.push_back((uint8_t)(v >> (8 * i))); };
+  DkimSig sig;
+  size_t cnt = 0;
+  for (const HeaderField& h : hs) {
+    if (!ieq_ascii(raw + h.key_off, h.key_len, "DKIM-Signature", 14)) continue;
+    cnt++;
+    if (validate_dkim_header(raw + h.val_off, h.val_len, now_unix, sig) != ZKB_DKIM_PASS) { put32(0); put32(0); put32(0); continue; }
+    const Tag* td = sig.get("d");
+    const Tag* ts = sig.get("s");
+    put32(1); put32(td->val_len); put32(ts->val_len);
+    buf.insert(buf.end(), sig.val(td), sig.val(td) + td->val_len);
+    buf.insert(buf.end(), sig.val(ts), sig.val(ts) + ts->val_len);
+  }
+  uint8_t* p = (uint8_t*)malloc(std::max<size_t>(1, buf.size()));
+  if (!p) return ZKB_E_NOMEM;
+  if (!buf.empty()) memcpy(p, buf.data(), buf.size());
+  *out = p; *out_len = buf.size(); *n_sigs = cnt;
   return ZKB_OK;
 }
 

@@ -144,7 +144,7 @@ EXPORTED_SYMBOLS = (
     "zkb_regex_compile", "zkb_free", "zkb_sha256_batch", "zkb_rsa_verify_batch",
     "zkb_dfa_scan_batch", "zkb_int_pipe_peaks", "zkb_host_canonicalize", "zkb_batch_device_flags",
     "zkb_host_register", "zkb_host_unregister", "zkb_engine_last_batch_bytes",
-    "zkb_abi_encode_batch", "zkb_abi_decode",
+    "zkb_abi_encode_batch", "zkb_abi_decode", "zkb_host_dkim_signatures",
 )
 
 _lib = None
@@ -435,6 +435,7 @@ class Engine:
     def __init__(self, device: int = 0, host_threads: int = 0, now_unix: int = 0,
                  chunk_emails: int = 0, rsa_lanes: int = 0):
         self.lib = load_library()
+        self.now_unix = now_unix
         opt = _Options(device, host_threads, now_unix, chunk_emails, 0, rsa_lanes)
         self.handle = C.c_void_p()
         _check(self.lib.zkb_engine_create(C.byref(opt), C.byref(self.handle)), "zkb_engine_create")
