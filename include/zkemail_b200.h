@@ -186,6 +186,12 @@ int zkb_batch_device_flags(const zkb_batch *b, size_t chunk, void **flags, size_
 int zkb_regex_compile(const char *pattern, size_t pattern_len, uint8_t **fwd, size_t *fwd_len,
                       uint8_t **bwd, size_t *bwd_len, char *err, size_t err_cap);
 void zkb_free(void *p);
+/* `DFA.fwd` / `DFA.bwd` may also hold regex-automata's own serialisation (dense::DFA::to_bytes_little_endian with the
+ * leading padding stripped, helpers/src/regex.rs:7-14): zkb_regex_set_create and zkb_dfa_scan_batch detect its label
+ * and convert it on load.  This entry point exposes the conversion (host-only): wire bytes -> malloc'ed ZDF1 table
+ * (free with zkb_free).  ZKB_E_REGEX when the blob does not validate — the engine's equivalent of
+ * dense::DFA::from_bytes(..).unwrap() panicking (core/src/regex.rs:32-33). */
+int zkb_regex_automata_to_zdf(const uint8_t *wire, size_t wire_len, int reverse, uint8_t **zdf, size_t *zdf_len);
 
 /* ---- host-only utility: cfdkim::canonicalize_signed_email (core/src/circuits.rs:34-35,
  * helpers/src/generator.rs:63) ----

@@ -10,6 +10,7 @@
 
 #include "../../include/zkemail_b200.h"
 #include "dfa.cuh"
+#include "ra_wire.hpp"
 
 namespace zkb {
 
@@ -92,6 +93,10 @@ inline bool build_dfa_blob(const uint8_t* zdf, size_t len, bool want_reverse, bo
 // for >= 8 CTAs of shared memory per SM, one element width for both.
 inline bool build_dfa_pair(const uint8_t* fwd, size_t fwd_len, const uint8_t* bwd, size_t bwd_len,
                            std::vector<uint8_t>& fb, std::vector<uint8_t>& rb, uint32_t& elem, bool& direct) {
+  // regex-automata wire blobs (what a Rust caller's DFA.fwd / DFA.bwd hold) are converted to ZDF1 first
+  std::vector<uint8_t> fz, rz;
+  if (ra::is_wire(fwd, fwd_len)) { if (!ra::to_zdf(fwd, fwd_len, false, fz)) return false; fwd = fz.data(); fwd_len = fz.size(); }
+  if (ra::is_wire(bwd, bwd_len)) { if (!ra::to_zdf(bwd, bwd_len, true, rz)) return false; bwd = rz.data(); bwd_len = rz.size(); }
   ZdfView f, r;
   if (!zdf_parse(fwd, fwd_len, f) || !zdf_parse(bwd, bwd_len, r)) return false;
   direct = ((uint64_t)f.n_states + r.n_states) * 257 * 2 <= 24 * 1024;

@@ -6,6 +6,7 @@
 #include <vector>
 #include "abi_pack.hpp"
 #include "dkim_host.hpp"
+#include "ra_wire.hpp"
 
 extern "C" {
 
@@ -83,6 +84,18 @@ int zkb_host_dkim_signatures(const uint8_t* raw, size_t n, int64_t now_unix, uin
   if (!p) return ZKB_E_NOMEM;
   if (!buf.empty()) memcpy(p, buf.data(), buf.size());
   *out = p; *out_len = buf.size(); *n_sigs = cnt;
+  return ZKB_OK;
+}
+
+int zkb_regex_automata_to_zdf(const uint8_t* wire, size_t wire_len, int reverse, uint8_t** zdf, size_t* zdf_len) {
+  if (!wire || !zdf || !zdf_len) return ZKB_E_INVALID;
+  *zdf = nullptr; *zdf_len = 0;
+  std::vector<uint8_t> z;
+  if (!zkb::ra::to_zdf(wire, wire_len, reverse != 0, z)) return ZKB_E_REGEX;
+  uint8_t* p = (uint8_t*)malloc(z.size());
+  if (!p) return ZKB_E_NOMEM;
+  memcpy(p, z.data(), z.size());
+  *zdf = p; *zdf_len = z.size();
   return ZKB_OK;
 }
 

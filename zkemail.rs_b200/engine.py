@@ -145,6 +145,7 @@ EXPORTED_SYMBOLS = (
     "zkb_dfa_scan_batch", "zkb_int_pipe_peaks", "zkb_host_canonicalize", "zkb_batch_device_flags",
     "zkb_host_register", "zkb_host_unregister", "zkb_engine_last_batch_bytes",
     "zkb_abi_encode_batch", "zkb_abi_decode", "zkb_host_dkim_signatures",
+    "zkb_regex_automata_to_zdf",
 )
 
 _lib = None
@@ -249,6 +250,20 @@ def _py_pattern(pattern: str) -> bytes:
         p = p.replace(f"[:{k}:]", v)
     p = p.replace(r"\z", r"\Z").replace("(?<", "(?P<") if "(?<=" not in p and "(?<!" not in p else p
     return p.encode("utf-8")
+
+
+def regex_automata_to_zdf(wire: bytes, reverse: bool) -> bytes:
+    """regex-automata dense-DFA bytes (helpers/src/regex.rs:7-14) -> the engine's ZDF1 table; raises RegexError
+    where dense::DFA::from_bytes would fail (core/src/regex.rs:32-33).  The engine does this itself on load."""
+    L = load_library()
+    L.zkb_regex_automata_to_zdf.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    out, n = C.c_void_p(), C.c_size_t()
+    if L.zkb_regex_automata_to_zdf(wire, len(wire), 1 if reverse else 0, C.byref(out), C.byref(n)) != 0:
+        raise RegexError("not a valid regex-automata dense DFA")
+    try:
+        return C.string_at(out.value, n.value)
+    finally:
+        L.zkb_free(out)
 
 
 def compile_regex_parts(parts: Sequence[RegexPattern], haystack: bytes) -> List[CompiledRegex]:
