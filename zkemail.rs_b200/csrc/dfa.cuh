@@ -128,6 +128,71 @@ struct Searcher {
   // instruction stream whatever its data looks like (a lane that branches on a per-byte event leaves the
   // convergent group; a lane that falls back to a byte-wise path makes its whole warp wait).  The dead state
   // is absorbing (row 0 is all zeros) and never a match, so finishing the block after dying is harmless.
+  // One aligned 16-byte block of a forward scan (requires o < n): advances (sid, c, o, skip) and records the
+  // last match position seen in the block.
+  template <bool QP>
+  __device__ __forceinline__ void fwd_block(uint32_t& sid, uint32_t& c, uint32_t& o, uint32_t& skip, bool& have, Cur& end, int& end_byte) {
+    const uint4* hb = reinterpret_cast<const uint4*>(h);
+    const uint32_t base = o & ~15u;
+    const uint32_t kend = (n - base) < 16u ? (n - base) : 16u;
+    const uint32_t mask = ((1u << kend) - 1u) & ~((1u << (o & 15u)) - 1u);   // bytes of this block in range
+    const uint4 v = __ldg(hb + (base >> 4));
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+    // bytes to drop: the tail of a soft break that started in the previous block, plus every "=\r\n"
+    // starting in this one.  Only blocks that contain '=' pay for the search (a short, rarely taken branch;
+    // the 16-step transition loop below is common to all lanes).
+    uint32_t drop = skip;
+    if (QP) {
+      const uint32_t e = 0x3d3d3d3du;
+      const uint32_t x0 = v.x ^ e, x1 = v.y ^ e, x2 = v.z ^ e, x3 = v.w ^ e;
+      const uint32_t z = ((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | ((x2 - 0x01010101u) & ~x2) | ((x3 - 0x01010101u) & ~x3);
+      if (z & 0x80808080u) {
+        uint32_t la = 0;   // the two bytes after the block (look-ahead for k = 14, 15)
+        if (base + 16 < n) la = __ldg(reinterpret_cast<const uint32_t*>(h + base + 16));
+        const uint32_t w5[5] = {v.x, v.y, v.z, v.w, la};
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          const uint32_t b0 = (w5[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+          const uint32_t b1 = (w5[(k + 1) >> 2] >> (((k + 1) & 3) * 8)) & 0xffu;
+          const uint32_t b2 = (w5[(k + 2) >> 2] >> (((k + 2) & 3) * 8)) & 0xffu;
+          const bool sb = b0 == '=' && b1 == '\r' && b2 == '\n' && base + k + 2 < n && ((mask >> k) & 1u);
+          drop |= sb ? (7u << k) : 0u;
+        }
+      }
+    }
+    skip = drop >> 16;                          // a soft break at k = 14 / 15 spills into the next block
+    const uint32_t cons = mask & ~drop;         // bytes the DFA consumes
+    int mk = -1;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const uint32_t b = (w4[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+      const bool act = (cons >> k) & 1u;
+      const uint32_t ns = f.next(sid, b);
+      sid = act ? ns : sid;
+      mk = (act && sid >= f.min_m && sid <= f.max_m) ? k : mk;
+    }
+    if (mk >= 0) {
+      have = true;
+      end.c = c + (uint32_t)__popc(cons & ((1u << mk) - 1u));
+      end.o = base + (uint32_t)mk;
+      const uint32_t w = (mk & 8) ? ((mk & 4) ? v.w : v.z) : ((mk & 4) ? v.y : v.x);
+      end_byte = (int)((w >> ((mk & 3) * 8)) & 0xffu);
+    }
+    c += (uint32_t)__popc(cons);
+    o = base + 16u;
+  }
+  // What follows the real bytes of a forward scan: virtual zero padding up to the original length (only bodies
+  // that had soft breaks get here with c < n), then the end-of-input transition.
+  __device__ __forceinline__ void fwd_tail(uint32_t sid, uint32_t c, uint32_t o, bool& have, Cur& end, int& end_byte) {
+    while (c < n && sid != 0 && o >= n) {
+      sid = f.next(sid, 0u);
+      if (sid >= f.min_m && sid <= f.max_m) { have = true; end.c = c; end.o = n; end_byte = 0; }
+      c++;
+    }
+    if (sid == 0) return;  // dead: the search ends with the last recorded match
+    sid = f.next_eoi(sid);
+    if (f.is_match(sid)) { have = true; end.c = n; end.o = n; end_byte = -1; }
+  }
   template <bool QP>
   __device__ bool fwd_impl(Cur from, int prev, Cur& end, int& end_byte) {
     if (from.c > n) return false;
@@ -135,66 +200,9 @@ struct Searcher {
     if (sid == 0) return false;
     bool have = false;
     uint32_t c = from.c, o = from.o, skip = 0;
-    const uint4* hb = reinterpret_cast<const uint4*>(h);
-    while (o < n && sid != 0) {
-      const uint32_t base = o & ~15u;
-      const uint32_t kend = (n - base) < 16u ? (n - base) : 16u;
-      const uint32_t mask = ((1u << kend) - 1u) & ~((1u << (o & 15u)) - 1u);   // bytes of this block in range
-      const uint4 v = __ldg(hb + (base >> 4));
-      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-      // bytes to drop: the tail of a soft break that started in the previous block, plus every "=\r\n"
-      // starting in this one.  Only blocks that contain '=' pay for the search (a short, rarely taken branch;
-      // the 16-step transition loop below is common to all lanes).
-      uint32_t drop = skip;
-      if (QP) {
-        const uint32_t e = 0x3d3d3d3du;
-        const uint32_t x0 = v.x ^ e, x1 = v.y ^ e, x2 = v.z ^ e, x3 = v.w ^ e;
-        const uint32_t z = ((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | ((x2 - 0x01010101u) & ~x2) | ((x3 - 0x01010101u) & ~x3);
-        if (z & 0x80808080u) {
-          uint32_t la = 0;   // the two bytes after the block (look-ahead for k = 14, 15)
-          if (base + 16 < n) la = __ldg(reinterpret_cast<const uint32_t*>(h + base + 16));
-          const uint32_t w5[5] = {v.x, v.y, v.z, v.w, la};
-#pragma unroll
-          for (int k = 0; k < 16; k++) {
-            const uint32_t b0 = (w5[k >> 2] >> ((k & 3) * 8)) & 0xffu;
-            const uint32_t b1 = (w5[(k + 1) >> 2] >> (((k + 1) & 3) * 8)) & 0xffu;
-            const uint32_t b2 = (w5[(k + 2) >> 2] >> (((k + 2) & 3) * 8)) & 0xffu;
-            const bool sb = b0 == '=' && b1 == '\r' && b2 == '\n' && base + k + 2 < n && ((mask >> k) & 1u);
-            drop |= sb ? (7u << k) : 0u;
-          }
-        }
-      }
-      skip = drop >> 16;                          // a soft break at k = 14 / 15 spills into the next block
-      const uint32_t cons = mask & ~drop;         // bytes the DFA consumes
-      int mk = -1;
-#pragma unroll
-      for (int k = 0; k < 16; k++) {
-        const uint32_t b = (w4[k >> 2] >> ((k & 3) * 8)) & 0xffu;
-        const bool act = (cons >> k) & 1u;
-        const uint32_t ns = f.next(sid, b);
-        sid = act ? ns : sid;
-        mk = (act && sid >= f.min_m && sid <= f.max_m) ? k : mk;
-      }
-      if (mk >= 0) {
-        have = true;
-        end.c = c + (uint32_t)__popc(cons & ((1u << mk) - 1u));
-        end.o = base + (uint32_t)mk;
-        const uint32_t w = (mk & 8) ? ((mk & 4) ? v.w : v.z) : ((mk & 4) ? v.y : v.x);
-        end_byte = (int)((w >> ((mk & 3) * 8)) & 0xffu);
-      }
-      c += (uint32_t)__popc(cons);
-      o = base + 16u;
-    }
+    while (o < n && sid != 0) fwd_block<QP>(sid, c, o, skip, have, end, end_byte);
     if (from.o < n && o >= n) clen = c;   // crossed the end of the real bytes: the cleaned length is known
-    // virtual zero padding up to the original length (only bodies that had soft breaks get here with c < n)
-    while (c < n && sid != 0 && o >= n) {
-      sid = f.next(sid, 0u);
-      if (sid >= f.min_m && sid <= f.max_m) { have = true; end.c = c; end.o = n; end_byte = 0; }
-      c++;
-    }
-    if (sid == 0) return have;  // dead: the search ends with the last recorded match
-    sid = f.next_eoi(sid);
-    if (f.is_match(sid)) { have = true; end.c = n; end.o = n; end_byte = -1; }
+    fwd_tail(sid, c, o, have, end, end_byte);
     return have;
   }
   __device__ __forceinline__ bool fwd(Cur from, int prev, Cur& end, int& end_byte) {
@@ -263,6 +271,58 @@ struct Searcher {
       last_end = me.c;
     }
   }
+  // find_iter for patterns that cannot match the empty string, as ONE loop over blocks: a lane whose search ends
+  // (dead state or end of input) books the match and starts its next search inside the same loop instead of
+  // leaving it, so the lanes of a warp - whose matches sit at different offsets - keep executing the block code
+  // together.  (With one loop per search the warp runs max(first search) + max(second search) block steps,
+  // about twice what each lane needs.)  The reverse scans that only produce match starts are deferred: the first
+  // and second match are resolved after the loop, later ones (already "not exactly one") on the spot, which keeps
+  // the count identical to running find() per match even for inconsistent forward / reverse tables.
+  // Returns false when an empty match shows up after all (tables whose flags lie): the caller then uses run().
+  template <bool QP>
+  __device__ bool run_flat(uint32_t& count, uint32_t& fs, uint32_t& fe, bool& panic) {
+    count = 0; fs = 0; fe = 0; panic = false;
+    clen = 0xffffffffu;
+    win_blk = 0xffffffffu;
+    Cur pos = begin();
+    int prev = -1;
+    const Cur from0 = pos;
+    Cur e1 = pos, e2 = pos, from2 = pos;
+    int b1 = -1, b2 = -1, prev2 = -1;
+    uint32_t sid = f.start(false, 2u), c = pos.c, o = pos.o, skip = 0, from_o = pos.o;
+    bool have = false, done = sid == 0;
+    Cur end = pos;
+    int end_byte = -1;
+    while (!done) {
+      if (o < n && sid != 0) { fwd_block<QP>(sid, c, o, skip, have, end, end_byte); continue; }
+      // this search is over
+      if (from_o < n && o >= n) clen = c;
+      fwd_tail(sid, c, o, have, end, end_byte);
+      if (!have) break;
+      if (end.c == pos.c) return false;   // empty match: not this path
+      if (count == 0) { e1 = end; b1 = end_byte; }
+      else if (count == 1) { e2 = end; b2 = end_byte; from2 = pos; prev2 = prev; }
+      else { uint32_t ms; if (!rev(pos, prev, end, end_byte, ms)) { panic = true; break; } }
+      count++;
+      // next search: from the match end, look-behind = the cleaned byte before it
+      Cur t = end;
+      prev = (int)back(t);
+      pos = end;
+      sid = f.start(false, f.smap[prev]);
+      c = pos.c; o = pos.o; skip = 0; from_o = pos.o; have = false;
+      done = sid == 0;
+    }
+    if (count >= 1) {
+      uint32_t ms;
+      if (!rev(from0, -1, e1, b1, ms)) { count = 0; panic = true; return true; }
+      fs = ms; fe = e1.c;
+    }
+    if (count >= 2) {
+      uint32_t ms;
+      if (!rev(from2, prev2, e2, b2, ms)) { count = 1; panic = true; }
+    }
+    return true;
+  }
 };
 
 #ifdef ZKB_HOST_EMU
@@ -297,7 +357,9 @@ __device__ __forceinline__ uint4 dfa_scan_one(const uint8_t* fb, const uint8_t* 
   s.f.init(fb); s.r.init(rb);
   s.h = hay; s.n = n; s.qp = qp != 0;
   uint32_t count, fs, fe; bool panic;
-  s.run(count, fs, fe, panic);
+  bool flat = false;
+  if (!(s.f.flags & ZKB_DFA_HAS_EMPTY)) flat = s.qp ? s.template run_flat<true>(count, fs, fe, panic) : s.template run_flat<false>(count, fs, fe, panic);
+  if (!flat) s.run(count, fs, fe, panic);
   return make_uint4(count, fs, fe, panic ? 1u : 0u);
 }
 

@@ -1080,7 +1080,9 @@ void resolve_email(const zkb_engine* e, const Chunk& ch, size_t i, const uint8_t
   const uint32_t* flags = (const uint32_t*)(outp + o_flags);
   auto put_digest = [&](uint8_t* dst, uint32_t gmsg) {
     const uint32_t* w = digests + (size_t)gmsg * 8;
-    for (int k = 0; k < 8; k++) { dst[4 * k] = (uint8_t)(w[k] >> 24); dst[4 * k + 1] = (uint8_t)(w[k] >> 16); dst[4 * k + 2] = (uint8_t)(w[k] >> 8); dst[4 * k + 3] = (uint8_t)w[k]; }
+    uint32_t be[8];
+    for (int k = 0; k < 8; k++) be[k] = __builtin_bswap32(w[k]);   // state words -> digest bytes
+    memcpy(dst, be, 32);
   };
   bool have_err = false, saw_sha1 = false, pass = false;
   int last_err = ZKB_DKIM_NEUTRAL;
@@ -1164,7 +1166,9 @@ bool resolve_email_fe(const zkb_engine* e, const Chunk& ch, size_t i, const uint
   const uint32_t f = ((const uint32_t*)(outp + o_flags))[gc];
   auto put_digest = [&](uint8_t* dst, uint32_t gmsg) {
     const uint32_t* w = digests + (size_t)gmsg * 8;
-    for (int k = 0; k < 8; k++) { dst[4 * k] = (uint8_t)(w[k] >> 24); dst[4 * k + 1] = (uint8_t)(w[k] >> 16); dst[4 * k + 2] = (uint8_t)(w[k] >> 8); dst[4 * k + 3] = (uint8_t)w[k]; }
+    uint32_t be[8];
+    for (int k = 0; k < 8; k++) be[k] = __builtin_bswap32(w[k]);   // state words -> digest bytes
+    memcpy(dst, be, 32);
   };
   put_digest(res.body_hash, t.msg_base + cd.body_msg);
   put_digest(res.header_hash, t.msg_base + cd.hdr_msg);
@@ -1430,7 +1434,18 @@ static double now_s() {
 // Pipelined end-to-end batch: pack chunk k+1 on the host while chunk k is on the device.
 static int verify_batch_impl(zkb_engine* e, const zkb_email_view* emails, size_t n, const zkb_regex_set* regex,
                              const zkb_email_captures* captures, zkb_result* out, bool allow_fe, std::vector<size_t>* fallback) {
-  const std::vector<size_t> bounds = chunk_bounds(emails, n, e->chunk_emails, (size_t)256 << 20);
+  // chunk size: at most chunk_emails messages and about 256 MB of raw bytes; batches of large messages get up to
+  // 1 GB per chunk so that a chunk still holds ~16 K messages (the per-message kernels map one lane to a message)
+  size_t max_bytes = (size_t)256 << 20;
+  if (n) {
+    size_t sample = 0;
+    const size_t step = n / 64 + 1;
+    size_t cnt = 0;
+    for (size_t i = 0; i < n; i += step) { sample += emails[i].raw_email_len; cnt++; }
+    const size_t avg = sample / cnt;
+    max_bytes = std::min<size_t>((size_t)1 << 30, std::max<size_t>(max_bytes, avg * 16384));
+  }
+  const std::vector<size_t> bounds = chunk_bounds(emails, n, e->chunk_emails, max_bytes);
   const size_t nchunks = bounds.size() - 1;
   std::vector<ThreadCtx> ctxs(e->pool->size());
   Chunk chunks[3];
