@@ -313,6 +313,10 @@ def main():
     ev1.synchronize()
     barrier()
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    # the verdicts of the timed (two-stream) schedule, checked against the generator's ground truth
+    res = pb.fetch()
+    exp_ok = pool.expected_ok()[order]
+    assert int(((res["status"] == 0) != exp_ok).sum()) == 0, "timed step: verdicts differ from the generator's ground truth"
     # per-kernel-family CUDA-event times on the engine stream (same launches, synchronous form)
     fam = []
     for _ in range(3):

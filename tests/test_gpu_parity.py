@@ -8,7 +8,7 @@ import pytest
 import oracle
 import zkemail_rs_b200 as z
 from zkemail_rs_b200 import synth
-from zkemail_rs_b200.structs import RegexInfo, RegexPattern
+from zkemail_rs_b200.structs import CompiledRegex, RegexInfo, RegexPattern
 from tests.util import NOW, assert_records_equal, key_pool, mixed_emails
 
 pytestmark = pytest.mark.gpu
@@ -154,6 +154,32 @@ def test_resident_batch_matches_pipeline(engine):
     pb.close()
     assert a.tobytes() == b.tobytes()
     assert st["n_emails"] == len(emails) and st["kernel_launches"] >= 3
+
+
+@pytest.mark.parametrize("knobs", [{}, {"ZKB_NO_OVERLAP": "1"}])
+def test_resident_multi_chunk_overlapped_schedule(monkeypatch, knobs):
+    """zkb_batch_run_async with several resident chunks: hashing of chunk k+1 on the side stream next to the RSA of
+    chunk k (and the single-stream order) gives the records of the plain pipeline and of the oracle."""
+    from zkemail_rs_b200.engine import EmailViews
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    eng = z.Engine(device=0, now_unix=NOW, chunk_emails=8)     # resident chunks hold 32 emails
+    try:
+        emails, _ = mixed_emails(seed=31, n_pos=150, with_token=True)
+        info = RegexInfo(None, [CompiledRegex(z.compile_regex(r"Transaction ID: [A-Z0-9]+"), None)])
+        views = EmailViews.from_emails(emails)
+        rs = z.RegexSet(eng, info)
+        pb = eng.prepare(views, rs, with_captures=False)
+        assert len(pb.device_flags()) >= 4
+        for _ in range(3):
+            pb.run_async()
+        got = pb.fetch()
+        pb.close()
+        exp = oracle.verify_batch(emails, None, info.body_parts, now=NOW)
+        for i, (g, e) in enumerate(zip(got, exp)):
+            assert_records_equal(g, e, i)
+    finally:
+        eng.close()
 
 
 def test_direct_mode_device_canonicalisation(engine):
