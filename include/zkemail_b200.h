@@ -182,7 +182,7 @@ int zkb_batch_device_flags(const zkb_batch *b, size_t chunk, void **flags, size_
 
 /* ---- regex compiler (stands in for helpers/src/regex.rs:7-51, which needs regex-automata) ----
  * Compiles `pattern` (Rust-regex syntax subset, Unicode/UTF-8 mode as DFARegex::new) to forward
- * and reverse ZDF1 tables.  On success *fwd/*bwd are malloc'ed; free with zkb_free. */
+ * and reverse ZDF1 tables.  On success *fwd and *bwd are malloc'ed; free with zkb_free. */
 int zkb_regex_compile(const char *pattern, size_t pattern_len, uint8_t **fwd, size_t *fwd_len,
                       uint8_t **bwd, size_t *bwd_len, char *err, size_t err_cap);
 void zkb_free(void *p);
