@@ -263,3 +263,21 @@ def test_front_end_paths_agree(engine, monkeypatch):
         assert_records_equal(staged[i], e, i)
         assert_records_equal(host[i], e, i)
         assert_records_equal(reg[i], e, i)
+
+
+def test_differential_fuzz_of_the_front_ends():
+    """tools/fuzz_frontend.py (dirty, mutated, multi-signature mail; device front end with host fallback vs oracle),
+    a fixed seed of it.  Larger runs: `python tools/fuzz_frontend.py 20000 <seed>` (60 000 mails checked in round 1)."""
+    import importlib.util
+    import os
+    import sys
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_frontend.py")
+    spec = importlib.util.spec_from_file_location("fuzz_frontend", path)
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    argv = sys.argv
+    sys.argv = ["fuzz_frontend.py", "3000", "11"]
+    try:
+        assert fz.main() == 0
+    finally:
+        sys.argv = argv
