@@ -58,8 +58,9 @@ struct DfaTab {
     if (DIRECT) return eoi[sid >> 8];
     return trans[sid + ncls - 1];
   }
-  // match ids form [min_m, max_m]; an empty range is encoded min_m > max_m
-  __device__ __forceinline__ bool is_match(uint32_t sid) const { return sid >= min_m && sid <= max_m; }
+  // the host numbers match states last (dfa_host.hpp): match <=> sid >= min_m; without match states min_m is
+  // above every id
+  __device__ __forceinline__ bool is_match(uint32_t sid) const { return sid >= min_m; }
   __device__ __forceinline__ uint32_t start(bool anchored, uint32_t kind) const { return hdr[6 + (anchored ? 6 : 0) + kind]; }
 };
 
@@ -165,11 +166,11 @@ struct Searcher {
     int mk = -1;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-      const uint32_t b = (w4[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+      const uint32_t b = __byte_perm(w4[k >> 2], 0u, 0x4440u + (uint32_t)(k & 3));   // one PRMT per byte
       const bool act = (cons >> k) & 1u;
       const uint32_t ns = f.next(sid, b);
       sid = act ? ns : sid;
-      mk = (act && sid >= f.min_m && sid <= f.max_m) ? k : mk;
+      mk = (act && f.is_match(sid)) ? k : mk;
     }
     if (mk >= 0) {
       have = true;
@@ -186,7 +187,7 @@ struct Searcher {
   __device__ __forceinline__ void fwd_tail(uint32_t sid, uint32_t c, uint32_t o, bool& have, Cur& end, int& end_byte) {
     while (c < n && sid != 0 && o >= n) {
       sid = f.next(sid, 0u);
-      if (sid >= f.min_m && sid <= f.max_m) { have = true; end.c = c; end.o = n; end_byte = 0; }
+      if (f.is_match(sid)) { have = true; end.c = c; end.o = n; end_byte = 0; }
       c++;
     }
     if (sid == 0) return;  // dead: the search ends with the last recorded match
@@ -217,7 +218,7 @@ struct Searcher {
     while (p.c > from.c && sid != 0) {
       uint32_t b = back(p);
       sid = r.next(sid, b);
-      if (sid >= r.min_m && sid <= r.max_m) { have = true; ms = p.c + 1; }
+      if (r.is_match(sid)) { have = true; ms = p.c + 1; }
     }
     if (sid == 0) return have;
     sid = prev_of_from < 0 ? r.next_eoi(sid) : r.next(sid, (uint32_t)prev_of_from);

@@ -60,13 +60,25 @@ inline bool build_dfa_blob(const uint8_t* zdf, size_t len, bool want_reverse, bo
   blob.assign((bytes + 15) & ~(size_t)15, 0);
   uint32_t* hdr = reinterpret_cast<uint32_t*>(blob.data());
   hdr[0] = d.n_states; hdr[1] = stride;
-  if (d.min_match <= d.max_match && d.max_match < d.n_states) {
-    hdr[2] = d.min_match * stride; hdr[3] = d.max_match * stride;
-  } else {  // no match states
-    hdr[2] = 1; hdr[3] = 0;
+  // Device numbering: the dead state stays 0, match states go LAST, so the per-byte match test of the scan is one
+  // compare (sid >= min_match).  perm[old] = new.
+  // (the dead state is never a match: the search stops on it before the match test, whatever the range says)
+  const uint32_t mlo = d.min_match ? d.min_match : 1u;
+  const bool has_match = mlo <= d.max_match && d.max_match < d.n_states;
+  std::vector<uint32_t> perm(d.n_states);
+  {
+    const uint32_t lo = has_match ? mlo : d.n_states, hi = has_match ? d.max_match : d.n_states;
+    const uint32_t n_match = has_match ? hi - lo + 1 : 0;
+    uint32_t next = 0;
+    for (uint32_t s = 0; s < d.n_states; s++) {
+      if (s >= lo && s <= hi) perm[s] = d.n_states - n_match + (s - lo);
+      else perm[s] = next++;
+    }
+    if (has_match) { hdr[2] = (d.n_states - n_match) * stride; hdr[3] = (d.n_states - 1) * stride; }
+    else { hdr[2] = 0xffffffffu; hdr[3] = 0xffffffffu; }   // no state id reaches this: never a match
   }
   hdr[4] = d.flags; hdr[5] = elem_bytes;
-  for (int i = 0; i < 12; i++) hdr[6 + i] = d.start[i] * stride;
+  for (int i = 0; i < 12; i++) hdr[6 + i] = perm[d.start[i]] * stride;
   hdr[18] = direct ? 1u : 0u;
   memcpy(blob.data() + 128, d.class_map, 256);
   memcpy(blob.data() + 384, d.start_map, 256);
@@ -76,14 +88,14 @@ inline bool build_dfa_blob(const uint8_t* zdf, size_t len, bool want_reverse, bo
   };
   // state 0 is the dead state: the search stops there and its transitions are never consulted by the
   // reference algorithm; the kernel relies on it being absorbing, so its row is forced to zeros
-  auto tr = [&](uint32_t s, uint32_t c) { return s == 0 ? 0u : rd32le(d.trans + 4 * ((uint64_t)s * d.n_classes + c)) * stride; };
+  auto tr = [&](uint32_t s, uint32_t c) { return s == 0 ? 0u : perm[rd32le(d.trans + 4 * ((uint64_t)s * d.n_classes + c))] * stride; };
   if (!direct) {
     for (uint32_t s = 0; s < d.n_states; s++)
-      for (uint32_t c = 0; c < d.n_classes; c++) put((uint64_t)s * stride + c, tr(s, c));
+      for (uint32_t c = 0; c < d.n_classes; c++) put((uint64_t)perm[s] * stride + c, tr(s, c));
   } else {
     for (uint32_t s = 0; s < d.n_states; s++) {
-      for (uint32_t b = 0; b < 256; b++) put((uint64_t)s * 256 + b, tr(s, d.class_map[b]));
-      put(cells + s, tr(s, d.n_classes - 1));
+      for (uint32_t b = 0; b < 256; b++) put((uint64_t)perm[s] * 256 + b, tr(s, d.class_map[b]));
+      put(cells + perm[s], tr(s, d.n_classes - 1));
     }
   }
   return true;
