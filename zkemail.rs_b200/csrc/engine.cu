@@ -198,9 +198,9 @@ struct DevBuf {  // growable device buffer
 // ------------------------------------------------------------------ records produced by the host pass
 struct MsgRec {         // one SHA-256 message / DFA haystack
   uint64_t goff;        // byte offset in the device arena (after layout)
-  uint32_t len, blk, local;  // blk == VIRT_BLK: a body canonicalised on the device; local = offset in the
-                             // thread's virtual region, len = raw length (upper-bound estimate), canon = its item
-  uint32_t canon;
+  uint32_t len, blk;    // blk == VIRT_BLK: a body canonicalised on the device; local = offset in the thread's
+  uint32_t canon;       // virtual region (resident chunks can exceed 4 GiB), len = raw length (upper-bound
+  uint64_t local;       // estimate), canon = its item; otherwise local = offset inside staging block blk
 };
 constexpr uint32_t VIRT_BLK = 0xFFFFFFFFu;
 enum { SIG_OK = 0, SIG_SYNTAX = 1, SIG_BADLEN = 2 };
@@ -384,7 +384,7 @@ struct ThreadCtx {
     it.l = l > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)l;
     it.msg = (uint32_t)tr->msgs.size();   // thread-local; made global at layout
     MsgRec m;
-    m.goff = 0; m.len = (uint32_t)body_len + 2; m.blk = VIRT_BLK; m.local = (uint32_t)tr->virt_used;
+    m.goff = 0; m.len = (uint32_t)body_len + 2; m.blk = VIRT_BLK; m.local = tr->virt_used;
     m.canon = (uint32_t)tr->canon.size();
     tr->virt_used += (((body_len + 2) >> 6) + 1) << 6;
     tr->canon.push_back(it);
@@ -685,7 +685,7 @@ void process_email_fe(ThreadCtx& c, const zkb_email_view& em, uint32_t local_idx
   }
   auto virt_msg = [&](size_t cap_len, uint32_t est_len) {
     MsgRec m;
-    m.goff = 0; m.len = est_len; m.blk = VIRT_BLK; m.local = (uint32_t)c.tr->virt_used; m.canon = 0;
+    m.goff = 0; m.len = est_len; m.blk = VIRT_BLK; m.local = c.tr->virt_used; m.canon = 0;
     c.tr->virt_used += ((cap_len >> 6) + 1) << 6;
     c.tr->msgs.push_back(m);
     const uint32_t nb = (est_len >> 6) + 1 + ((est_len & 63) >= 56 ? 1u : 0u);
@@ -713,7 +713,7 @@ inline double now_s2() { return std::chrono::duration<double>(std::chrono::stead
 // Host pack of emails [e0, e0+ne): parallel parse + layout of the SoA meta buffers.
 // ctxs: one ThreadCtx per pool thread, alive for the whole API call (key lookups are cached across chunks)
 int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne, const zkb_regex_set* rs, Chunk& ch, PinBuf& pin_meta,
-               std::vector<ThreadCtx>& ctxs, bool allow_fe = false) {
+               std::vector<ThreadCtx>& ctxs, bool allow_fe = false, size_t max_span = (size_t)3 << 30) {
   const int T = e->pool->size();
   ch.e0 = e0; ch.ne = ne; ch.views = emails + e0;
   ch.emails.assign(ne, EmailRec());
@@ -737,7 +737,7 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
     }
     for (auto& r : e->registered) {
       if (lo >= r.first && hi <= r.first + r.second && (size_t)(hi - lo) <= payload + payload / 2 + (1u << 20) &&
-          (size_t)(hi - lo) < ((size_t)3 << 30)) {
+          (size_t)(hi - lo) < max_span) {
         const uint8_t* base = (const uint8_t*)((uintptr_t)lo & ~(uintptr_t)255);
         if (base < r.first) base = r.first;
         ch.direct = true; ch.span_host = base; ch.span_bytes = (size_t)(hi - base);
@@ -1598,8 +1598,18 @@ int zkb_batch_prepare(zkb_engine* e, const zkb_email_view* emails, size_t n, con
   CK(cudaSetDevice(e->device));
   zkb_batch* b = new zkb_batch();
   b->eng = e; b->regex = regex; b->n = n; b->emails = emails; b->captures = captures;
-  // resident batches: fewer, larger launches (better SM balance; nothing to overlap with)
-  const std::vector<size_t> bounds = chunk_bounds(emails, n, e->chunk_emails * 4, (size_t)3 << 30);
+  // resident batches: fewer, larger launches (better SM balance).  When the whole batch lies in registered memory
+  // (raw bytes are DMA'd, nothing is staged in pinned blocks) a chunk may hold up to 16 GB, so that batches of large
+  // messages still give the lane-per-message kernels tens of thousands of lanes per launch (100 KB bodies: 29 K
+  // lanes per 3 GB chunk left the SHA-256 kernel latency-bound at 1.5 warps per scheduler).
+  size_t max_bytes = (size_t)3 << 30;
+  if (n && !e->registered.empty() && !getenv("ZKB_NO_DIRECT")) {
+    const uint8_t *lo = emails[0].raw_email, *hi = lo;
+    for (size_t i = 0; i < n; i++) { lo = std::min(lo, emails[i].raw_email); hi = std::max(hi, emails[i].raw_email + emails[i].raw_email_len); }
+    for (auto& r : e->registered)
+      if (lo >= r.first && hi <= r.first + r.second) { max_bytes = (size_t)16 << 30; break; }
+  }
+  const std::vector<size_t> bounds = chunk_bounds(emails, n, e->chunk_emails * 4, max_bytes);
   std::vector<ThreadCtx> ctxs(e->pool->size());
   cudaStream_t s = e->slots[0].stream;
   int rc = ZKB_OK;
@@ -1607,7 +1617,7 @@ int zkb_batch_prepare(zkb_engine* e, const zkb_email_view* emails, size_t n, con
     Chunk* ch = new Chunk();
     DeviceChunk* d = new DeviceChunk();
     b->chunks.push_back(ch); b->dev.push_back(d);
-    rc = pack_chunk(e, emails, bounds[k], bounds[k + 1] - bounds[k], regex, *ch, e->slots[0].meta, ctxs);
+    rc = pack_chunk(e, emails, bounds[k], bounds[k + 1] - bounds[k], regex, *ch, e->slots[0].meta, ctxs, false, max_bytes + ((size_t)1 << 30));
     if (rc) break;
     rc = sync_keytab(e, s);
     if (rc) break;
