@@ -8,7 +8,7 @@ from .engine import (  # noqa: F401,E402
     Engine, EngineUnavailable, RegexError, RegexSet, VerificationPanic, compile_regex,
     canonicalize_signed_email, compile_regex_parts, verify_email, verify_email_with_regex,
 )
-from .io import AbiDecodeError, VerificationOutput, abi_decode, abi_encode_batch  # noqa: F401,E402
+from .abi_io import AbiDecodeError, VerificationOutput, abi_decode, abi_encode_batch  # noqa: F401,E402
 from .generator import (  # noqa: F401,E402
     GeneratorError, StaticKeys, dkim_signatures, generate_email_inputs, generate_email_inputs_batch,
     generate_email_with_regex_inputs, parse_dkim_key_record, remove_quoted_printable_soft_breaks,
