@@ -281,3 +281,30 @@ def test_differential_fuzz_of_the_front_ends():
         assert fz.main() == 0
     finally:
         sys.argv = argv
+
+
+def test_concurrent_callers(engine):
+    """calls on one engine are serialised, distinct engines are independent — four threads, two
+    engines, every result identical to the single-threaded one."""
+    import threading
+    emails, _ = mixed_emails(seed=41, n_pos=40)
+    ref = engine.verify_batch(emails).tobytes()
+    other = z.Engine(device=0, now_unix=NOW, host_threads=2)
+    errs = []
+
+    def work(eng, rounds):
+        try:
+            for _ in range(rounds):
+                assert eng.verify_batch(emails).tobytes() == ref
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    try:
+        ts = [threading.Thread(target=work, args=(engine if i % 2 == 0 else other, 6)) for i in range(4)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+    finally:
+        other.close()
+    assert not errs, errs
