@@ -26,8 +26,9 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def sha256_batch(msgs):
-    """The SHA-256 kernel source over a packed arena (garbage in the padding), sorted order."""
+def sha256_batch(msgs, prefetch=False):
+    """The SHA-256 kernel source over a packed arena (garbage in the padding), sorted order.
+    prefetch=True runs the double-buffered instantiation used for launches with few lanes."""
     n = len(msgs)
     off, cur = [], 0
     for m in msgs:
@@ -40,7 +41,7 @@ def sha256_batch(msgs):
     lena = np.array([len(m) for m in msgs], dtype=np.uint32)
     order = np.argsort(-lena.astype(np.int64), kind="stable").astype(np.uint32)
     dig = np.zeros((n, 8), dtype=np.uint32)
-    lib().emu_sha256_batch(_p(arena), _p(offa), _p(lena), _p(order), n, _p(dig))
+    (lib().emu_sha256_batch_prefetch if prefetch else lib().emu_sha256_batch)(_p(arena), _p(offa), _p(lena), _p(order), n, _p(dig))
     return [dig[i].astype(">u4").tobytes() for i in range(n)]
 
 

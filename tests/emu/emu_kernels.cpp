@@ -32,7 +32,14 @@ void emu_sha256_batch(const uint8_t* arena, const uint64_t* off, const uint32_t*
                       const uint32_t* order, uint32_t n, uint32_t* digests) {
   const unsigned block = 128;
   emu::launch((n + block - 1) / block, block,
-              [&]() { sha256_batch_kernel(arena, off, len, order, n, digests, 1u); });
+              [&]() { sha256_batch_kernel<false>(arena, off, len, order, n, digests, 1u); });
+}
+// the variant that requests block b+1 before compressing block b (launches with few lanes)
+void emu_sha256_batch_prefetch(const uint8_t* arena, const uint64_t* off, const uint32_t* len,
+                               const uint32_t* order, uint32_t n, uint32_t* digests) {
+  const unsigned block = 128;
+  emu::launch((n + block - 1) / block, block,
+              [&]() { sha256_batch_kernel<true>(arena, off, len, order, n, digests, 1u); });
 }
 
 // key DER -> key-table entry (ZKB_KEY_STRIDE words). returns 0 ok, 1 rejected

@@ -21,9 +21,10 @@ def test_sha256_kernel_source():
     lens = [0, 1, 3, 55, 56, 57, 63, 64, 65, 119, 120, 127, 128, 129, 4096, 4097, 520, 1000]
     lens += [int(x) for x in rng.integers(0, 700, size=110)]
     msgs = [rng.integers(0, 256, size=l, dtype=np.uint8).tobytes() for l in lens]
-    got = emu.sha256_batch(msgs)
-    for m, g in zip(msgs, got):
-        assert g == hashlib.sha256(m).digest(), len(m)
+    for prefetch in (False, True):
+        got = emu.sha256_batch(msgs, prefetch=prefetch)
+        for m, g in zip(msgs, got):
+            assert g == hashlib.sha256(m).digest(), (len(m), prefetch)
 
 
 def _rsa_cases(bits, n):

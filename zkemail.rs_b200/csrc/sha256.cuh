@@ -66,6 +66,10 @@ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16], 
 // msg_off: byte offsets into arena, 16-byte aligned; every message slot must be readable up to
 // the next 64-byte boundary past its end (the packer guarantees it).  order: optional
 // permutation (message ids sorted by block count).  digests: n x 8 native state words.
+// PREFETCH: the 64 bytes of block b+1 are requested before block b is compressed.  Used when the launch has few
+// lanes (large bodies): with ~5 warps per scheduler the load latency at the top of every block is not hidden by
+// other warps.  Costs 16 registers, so launches with many lanes (occupancy-bound) use the plain variant.
+template <bool PREFETCH>
 __global__ void __launch_bounds__(128)
 sha256_batch_kernel(const uint8_t* __restrict__ arena, const uint64_t* __restrict__ msg_off,
                     const uint32_t* __restrict__ msg_len, const uint32_t* __restrict__ order,
@@ -79,11 +83,20 @@ sha256_batch_kernel(const uint8_t* __restrict__ arena, const uint64_t* __restric
   uint32_t total = nfull + 1 + (rem >= 56 ? 1 : 0);
   uint32_t st[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a,
                     0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+  uint4 n0, n1, n2, n3;   // PREFETCH: the next block's bytes (block 0 first; the slot is readable past nfull)
+  if (PREFETCH) { n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3); }
   for (uint32_t blk = 0; blk < total; blk++) {
     uint32_t w[16];
     if (blk <= nfull) {
-      uint4 v0 = __ldg(p + 4 * blk), v1 = __ldg(p + 4 * blk + 1), v2 = __ldg(p + 4 * blk + 2),
-            v3 = __ldg(p + 4 * blk + 3);
+      uint4 v0, v1, v2, v3;
+      if (PREFETCH) {
+        v0 = n0; v1 = n1; v2 = n2; v3 = n3;
+        if (blk < nfull) {
+          n0 = __ldg(p + 4 * blk + 4); n1 = __ldg(p + 4 * blk + 5); n2 = __ldg(p + 4 * blk + 6); n3 = __ldg(p + 4 * blk + 7);
+        }
+      } else {
+        v0 = __ldg(p + 4 * blk); v1 = __ldg(p + 4 * blk + 1); v2 = __ldg(p + 4 * blk + 2); v3 = __ldg(p + 4 * blk + 3);
+      }
       w[0] = bswap32(v0.x); w[1] = bswap32(v0.y); w[2] = bswap32(v0.z); w[3] = bswap32(v0.w);
       w[4] = bswap32(v1.x); w[5] = bswap32(v1.y); w[6] = bswap32(v1.z); w[7] = bswap32(v1.w);
       w[8] = bswap32(v2.x); w[9] = bswap32(v2.y); w[10] = bswap32(v2.z); w[11] = bswap32(v2.w);
