@@ -1459,8 +1459,9 @@ static double now_s() {
 // Pipelined end-to-end batch: pack chunk k+1 on the host while chunk k is on the device.
 static int verify_batch_impl(zkb_engine* e, const zkb_email_view* emails, size_t n, const zkb_regex_set* regex,
                              const zkb_email_captures* captures, zkb_result* out, bool allow_fe, std::vector<size_t>* fallback) {
-  // chunk size: at most chunk_emails messages and about 256 MB of raw bytes; batches of large messages get up to
-  // 1 GB per chunk so that a chunk still holds ~16 K messages (the per-message kernels map one lane to a message)
+  // chunk size: at most chunk_emails messages and about 256 MB of raw bytes; batches of larger messages get up to
+  // 1 GB per chunk so that a chunk still holds tens of thousands of messages (the per-message kernels map one lane
+  // to a message: 16 K-message chunks of the mixed-size sweep left them latency-bound and the pipeline kernel-bound)
   size_t max_bytes = (size_t)256 << 20;
   if (n) {
     size_t sample = 0;
@@ -1468,7 +1469,7 @@ static int verify_batch_impl(zkb_engine* e, const zkb_email_view* emails, size_t
     size_t cnt = 0;
     for (size_t i = 0; i < n; i += step) { sample += emails[i].raw_email_len; cnt++; }
     const size_t avg = sample / cnt;
-    max_bytes = std::min<size_t>((size_t)1 << 30, std::max<size_t>(max_bytes, avg * 16384));
+    max_bytes = std::min<size_t>((size_t)1 << 30, std::max<size_t>(max_bytes, avg * e->chunk_emails));
   }
   const std::vector<size_t> bounds = chunk_bounds(emails, n, e->chunk_emails, max_bytes);
   const size_t nchunks = bounds.size() - 1;
