@@ -249,7 +249,9 @@ def test_front_end_paths_agree(engine, monkeypatch):
     emails, _ = mixed_emails(seed=17, n_pos=48)
     exp = oracle.verify_batch(emails, now=NOW)
     staged = engine.verify_batch(emails)
-    assert engine.last_batch_bytes()["h2d_bytes"] > sum(len(e.raw_email) for e in emails)   # raw messages travelled
+    import os
+    if not (os.environ.get("ZKB_NO_DEVICE_FRONTEND") or os.environ.get("ZKB_NO_STAGED_FRONTEND")):
+        assert engine.last_batch_bytes()["h2d_bytes"] > sum(len(e.raw_email) for e in emails)   # raw messages travelled
     monkeypatch.setenv("ZKB_NO_DEVICE_FRONTEND", "1")
     host = engine.verify_batch(emails)
     monkeypatch.delenv("ZKB_NO_DEVICE_FRONTEND")
