@@ -10,10 +10,12 @@ Steps (reference call sites in brackets): read the message [helpers/src/file.rs:
 EmailWithRegex inputs offline [helpers/src/generator.rs:11-87], verify on the GPU [core/src/circuits.rs:9,31],
 ABI-encode the output [core/src/io.rs:35].  Needs a B200; there is no CPU fallback."""
 import json
+import os
 import sys
 
-import zkemail_rs_b200 as z
-from zkemail_rs_b200.structs import RegexConfig
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import zkemail_rs_b200 as z  # noqa: E402
+from zkemail_rs_b200.structs import RegexConfig  # noqa: E402
 
 
 def main(argv):
