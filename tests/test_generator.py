@@ -144,3 +144,29 @@ def test_generate_email_with_regex_inputs_round_trip(engine):
                                            RegexConfig(body_parts=[RegexPattern(r"[A-Z]", None)]), keys, engine=engine)
     empty = z.generate_email_with_regex_inputs("shop.example.com", e.raw_email, RegexConfig(header_parts=[], body_parts=None), keys, engine=engine)
     assert empty.regex_info.header_parts is None and empty.regex_info.body_parts is None
+
+
+@pytest.mark.gpu
+def test_example_script_on_files(tmp_path):
+    """examples/verify_eml.py: .eml + key records + RegexConfig JSON in, serde JSON + ABI bytes out."""
+    import json
+    import os
+    import subprocess
+    import sys
+    rng = np.random.default_rng(12)
+    k = key_pool()[2048][1]
+    e = synth.make_email(rng, k, "files.example.com", idx=5, body_len=600, token=b"Transaction ID: F00D1234")
+    (tmp_path / "m.eml").write_bytes(e.raw_email)
+    (tmp_path / "keys.json").write_text(json.dumps({"sel1": _txt(_spki(k.der))}))
+    (tmp_path / "regex.json").write_text(json.dumps({"header_parts": None, "body_parts": [{"pattern": "Transaction ID: ([A-Z0-9]+)", "capture_indices": [1]}]}))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "verify_eml.py"), str(tmp_path / "m.eml"), "files.example.com",
+                          str(tmp_path / "keys.json"), str(tmp_path / "regex.json")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.strip().splitlines()
+    res = z.from_serde(z.EmailWithRegexVerifierOutput, json.loads(lines[0]))
+    assert res.regex_matches == ["F00D1234"]
+    exp = oracle.verify_batch([e], now=0)[0]
+    assert res.email.from_domain_hash == exp["from_domain_hash"] and res.email.public_key_hash == exp["public_key_hash"]
+    blob = bytes.fromhex(lines[1].split("abi:", 1)[1].strip())
+    assert z.abi_decode(blob).matches == ["F00D1234"]
