@@ -138,7 +138,7 @@ void emu_canon_body(const uint8_t* span, const uint64_t* off, const uint32_t* le
 // Device front end (frontend.cuh: fe_process) against the host front end (dkim_host.hpp) on one message.
 // returns 0 = the device path declines (fallback), 1 = live and identical to the host, 2 = both report a
 // mail parse error, negative = MISMATCH (code tells which field).
-int emu_fe_compare(const uint8_t* raw_in, uint32_t n, const uint8_t* dom, uint32_t dom_len, uint32_t k, uint32_t limbs) {
+int emu_fe_compare(const uint8_t* raw_in, uint32_t n, const uint8_t* dom, uint32_t dom_len, uint32_t k, uint32_t limbs, int allow_skip) {
   // the device reads whole aligned 16-byte blocks: give it the message at an odd offset inside a padded buffer
   std::vector<uint8_t> padded((size_t)n + 96, 0x3B);
   uint8_t* raw = padded.data() + 16 + ((16 - ((uintptr_t)padded.data() & 15)) & 15) + 5;
@@ -146,7 +146,7 @@ int emu_fe_compare(const uint8_t* raw_in, uint32_t n, const uint8_t* dom, uint32
   std::vector<uint8_t> pre(FE_PRE_CAP + 64, 0xEE);
   std::vector<uint32_t> sigw(limbs, 0xDEADBEEFu);
   FeOut fo;
-  fe_process(raw, n, dom, dom_len, k, limbs, pre.data(), sigw.data(), fo);
+  fe_process(raw, n, dom, dom_len, k, limbs, pre.data(), sigw.data(), fo, allow_skip != 0);
   std::vector<HeaderField> hs;
   size_t body_off = 0;
   const bool parsed = parse_headers(raw, n, hs, body_off);
@@ -157,12 +157,20 @@ int emu_fe_compare(const uint8_t* raw_in, uint32_t n, const uint8_t* dom, uint32
   DkimSig sig;
   std::string scratch;
   int n_sig = 0, idx = -1;
-  for (size_t i = 0; i < hs.size(); i++)
-    if (ieq_ascii(raw + hs[i].key_off, hs[i].key_len, "DKIM-Signature", 14)) { n_sig++; idx = (int)i; }
-  if (n_sig != 1) return -3;
-  if (validate_dkim_header(raw + hs[idx].val_off, hs[idx].val_len, 1, sig) != ZKB_DKIM_PASS) return -4;
-  const Tag* td = sig.get("d");
-  if (!ieq_ascii(sig.val(td), td->val_len, (const char*)dom, dom_len)) return -5;
+  // the reference's walk over the DKIM-Signature headers (cfdkim::verify_email_with_key): headers of another domain
+  // are skipped; the device may only have gone past headers that validate, and must have stopped at the first
+  // header of `dom`
+  for (size_t i = 0; i < hs.size(); i++) {
+    if (!ieq_ascii(raw + hs[i].key_off, hs[i].key_len, "DKIM-Signature", 14)) continue;
+    n_sig++;
+    if (idx >= 0) continue;
+    if (validate_dkim_header(raw + hs[i].val_off, hs[i].val_len, 1, sig) != ZKB_DKIM_PASS) return -4;
+    const Tag* tdd = sig.get("d");
+    if (ieq_ascii(sig.val(tdd), tdd->val_len, (const char*)dom, dom_len)) idx = (int)i;
+    else if (!allow_skip) return -3;
+  }
+  if (idx < 0) return -5;
+  if (((fo.flags & FE_MULTI) != 0) != (n_sig > 1)) return -18;
   bool hr, br;
   if (!parse_canon_tag(sig, hr, br)) return -6;
   if (!sig.val_is(sig.get("a"), "rsa-sha256")) return -7;

@@ -228,8 +228,8 @@ def test_canon_body_kernel_source_vs_oracle():
                 assert g == oracle.canon_body(b, relaxed)[:l], (relaxed, l, b, g)
 
 
-def _fe_compare(raw: bytes, dom: bytes, k=256, limbs=64) -> int:
-    return emu.lib().emu_fe_compare(raw, len(raw), dom, len(dom), k, limbs)
+def _fe_compare(raw: bytes, dom: bytes, k=256, limbs=64, allow_skip=False) -> int:
+    return emu.lib().emu_fe_compare(raw, len(raw), dom, len(dom), k, limbs, 1 if allow_skip else 0)
 
 
 def test_device_front_end_source_on_synthetic_mail():
@@ -262,9 +262,10 @@ _FE_B = st.sampled_from([b"QUJD\r\n\t REVG", b"QUJDREVG", b"QUJDRA==", b"QUJ", b
        st.sampled_from(["relaxed/relaxed", "simple/simple", "relaxed/simple", "simple/relaxed", "relaxed", "simple", "bogus", None]),
        st.lists(st.sampled_from(["from", "to", "subject", "date", "cc", "x-test", "From", "message-id", "missing", "subject "]), min_size=0, max_size=6),
        st.sampled_from(["", " l=5;", " i=@example.com;", " x=99999999999;", " q=dns/txt;", " z=1;", " v=2;", " d=other.org;", " a=rsa-sha1;"]),
-       _FE_B, st.sampled_from(["top", "bottom", "both"]),
-       st.sampled_from([b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA=", b"AAAA", b"AAAAAAAAAAAAAAAAAAAAAA\r\n\tAAAAAAAAAAAAAAAAAAAAA="]))
-def test_device_front_end_source_on_dirty_mail(headers, body, canon, hnames, extra, bval, where, bh):
+       _FE_B, st.sampled_from(["top", "bottom", "both", "foreign", "foreign", "foreign_sha1", "foreign_after"]),
+       st.sampled_from([b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA=", b"AAAA", b"AAAAAAAAAAAAAAAAAAAAAA\r\n\tAAAAAAAAAAAAAAAAAAAAA="]),
+       st.booleans())
+def test_device_front_end_source_on_dirty_mail(headers, body, canon, hnames, extra, bval, where, bh, allow_skip):
     """Whatever the device front end accepts must equal the host front end byte for byte; anything it
     does not accept must be flagged for the host (never a silent difference)."""
     block = b"".join(k + s + v.rstrip(b"\r\n\t ") + b"\r\n" if not v.endswith((b"\r\n ", b"\r\n\t", b"\n ")) else k + s + v + b"x\r\n"
@@ -272,15 +273,43 @@ def test_device_front_end_source_on_dirty_mail(headers, body, canon, hnames, ext
     h = ":".join(["from"] + hnames)
     ctag = f" c={canon};" if canon else ""
     sig = (f"DKIM-Signature: v=1; a=rsa-sha256;{ctag} d=example.com; s=s;\r\n\th={h};{extra}\r\n\tbh=").encode() + bh + b";\r\n\tb=" + bval + b"\r\n"
+    foreign = b"DKIM-Signature: v=1; a=rsa-sha256; c=relaxed/relaxed; d=Other.org; s=x;\r\n\th=from:to;\r\n\tbh=" + bh + b";\r\n\tb=QUJD\r\n"
     if where == "top":
         raw = sig + block
     elif where == "bottom":
         raw = block + sig
+    elif where == "foreign":          # a signature of another domain first: skipped by the reference
+        raw = foreign + block + sig
+    elif where == "foreign_sha1":     # one the device cannot judge: must fall back
+        raw = foreign.replace(b"rsa-sha256", b"rsa-sha1") + sig + block
+    elif where == "foreign_after":
+        raw = sig + block + foreign
     else:
         raw = sig + block + sig
     raw += b"\r\n" + body
-    r = _fe_compare(raw, b"Example.COM", k=6, limbs=32)
+    r = _fe_compare(raw, b"Example.COM", k=6, limbs=32, allow_skip=allow_skip)
     assert r >= 0, (r, raw)
+    if where == "foreign_sha1" or (where == "foreign" and not allow_skip):
+        assert r in (0, 2), (r, raw)
+
+
+def test_device_front_end_skips_foreign_signatures_only_when_allowed():
+    from tests.util import mixed_emails
+    from zkemail_rs_b200 import synth
+    emails, labels = mixed_emails(seed=23)
+    good = [e for e, lab in zip(emails, labels) if lab == "pos"][:6]
+    other = synth.make_email(np.random.default_rng(4), key_pool()[2048][1], "elsewhere.example.org", idx=9, body_len=80).raw_email
+    foreign = other[: other.find(b"\r\n", other.find(b"\tb=")) + 2]
+    assert foreign.startswith(b"DKIM-Signature")
+    for e in good:
+        big = len(e.public_key.key) > 200
+        args = (e.from_domain.encode(), 256 if big else 128, 64 if big else 32)
+        top = e.raw_email.startswith(b"DKIM-Signature")
+        assert _fe_compare(foreign + e.raw_email, *args, allow_skip=True) == 1
+        assert _fe_compare(foreign + e.raw_email, *args, allow_skip=False) == 0
+        if top:   # candidate first, foreign signature later: fine with regex parts as well
+            cut = e.raw_email.find(b"\r\n", e.raw_email.find(b"\tb=")) + 2
+            assert _fe_compare(e.raw_email[:cut] + foreign + e.raw_email[cut:], *args, allow_skip=False) == 1
 
 
 def test_regex_unicode_perl_classes():

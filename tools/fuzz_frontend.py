@@ -26,11 +26,21 @@ EXTRA = ["", "", "", " t=1700000000;", " i=@d.example.com;", " i=user@sub.d.exam
          " x=1;", " z=From:a|To:b;", " q=other;", " i=@elsewhere.org;"]
 
 
+def _insert_after_headers(raw, extra):
+    i = raw.find(b"\r\n\r\n")
+    return raw if i < 0 else raw[:i + 2] + extra + raw[i + 2:]
+
+
 def build(n, seed):
     rng = np.random.default_rng(seed)
     keys = key_pool()[1024][:4]
     pick = lambda xs: xs[int(rng.integers(0, len(xs)))]  # noqa: E731
     emails = []
+    foreign = []   # signature headers of other domains (the reference skips them; the device may too)
+    for j in range(6):
+        o = synth.make_email(rng, pick(keys), f"other{j}.example.org", idx=j, body_len=40,
+                             canon=pick(CANON[:4]), **({"algo": "rsa-sha1"} if j == 5 else {})).raw_email
+        foreign.append(o[: o.find(b"\r\n", o.find(b"\tb=")) + 2])
     while len(emails) < n:
         k = pick(keys)
         dom = "d.example.com"
@@ -66,6 +76,9 @@ def build(n, seed):
             e = z.Email(pick(["D.EXAMPLE.COM", "example.com", "x.d.example.com"]), raw, e.public_key)
         elif r == 4:
             e = z.Email(dom, raw, z.PublicKey(pick(keys).der, "rsa"))
+        elif r in (5, 6):          # signature header(s) of other domains in front of / behind the real one
+            f = b"".join(pick(foreign) for _ in range(int(rng.integers(1, 3))))
+            e = z.Email(dom, f + raw if r == 5 else raw + b"", e.public_key) if r == 5 else z.Email(dom, _insert_after_headers(raw, f), e.public_key)
         emails.append(e)
     return emails
 

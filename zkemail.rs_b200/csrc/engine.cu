@@ -1013,7 +1013,8 @@ int launch_chunk(zkb_engine* e, const DeviceChunk& d, const zkb_regex_set* rs, c
   uint64_t nl = 0;
   const bool pre = phase != 2, rsa = phase != 1;
   if (pre && d.n_fe) {
-    launch_frontend(d.raw_base, d.fe_in, d.n_fe, d.arena.p, d.msg_off, d.msg_len_rw, d.sig_rw, d.cand_bh_rw, d.canon_rw, d.fe_out, s);
+    // without regex parts, signature headers of other domains in front of the candidate may be skipped on the device
+    launch_frontend(d.raw_base, d.fe_in, d.n_fe, d.arena.p, d.msg_off, d.msg_len_rw, d.sig_rw, d.cand_bh_rw, d.canon_rw, d.fe_out, rs == nullptr, s);
     nl++;
   }
   if (pre && d.n_canon) { launch_canon_body(d.raw_base, d.canon_items, d.n_canon, d.arena.p, d.msg_off, d.msg_len_rw, s); nl++; }
@@ -1191,6 +1192,8 @@ bool resolve_email_fe(const zkb_engine* e, const Chunk& ch, size_t i, const uint
   if (!res.bh_ok) detail = ZKB_DKIM_BODY_HASH;
   else if (fo.flags & FE_SIG_SYNTAX) detail = ZKB_DKIM_SIG_SYNTAX;
   else if ((fo.flags & FE_SIG_BADLEN) || !(f & ZKB_F_RSA_OK)) detail = ZKB_DKIM_SIG_MISMATCH;
+  // several signature headers: the reference would go on to the later ones; only a pass is final here
+  if (detail != ZKB_DKIM_PASS && (fo.flags & FE_MULTI)) return false;
   res.dkim_detail = detail;
   if (detail != ZKB_DKIM_PASS) { res.status = ZKB_ST_DKIM_FAIL; return true; }
   res.rsa_ok = 1;

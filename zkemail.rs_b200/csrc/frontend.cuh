@@ -2,7 +2,7 @@
 // rank 1): for messages that sit in registered host memory the raw bytes are DMA'd as they are and one
 // thread per message does, on the device, what dkim_host.hpp does on the host threads for the common
 // well-formed case:
-//   mailparse header split -> the single DKIM-Signature header -> tag list -> required tags, v=1,
+//   mailparse header split -> the first DKIM-Signature header of from_domain -> tag list -> required tags, v=1,
 //   d= == from_domain, c=, a=rsa-sha256 -> signed-header selection per h= (bottom-up, repeated names walk
 //   upward) -> relaxed/simple header canonicalisation -> the b=-blanked DKIM-Signature header without its
 //   final CRLF (the header-hash preimage, written into the arena slot the SHA-256 kernel reads) ->
@@ -10,7 +10,11 @@
 // Reference behaviour: cfdkim::verify_email_with_key / validate_header / select_headers
 // (core/src/email.rs:31-33).
 //
-// Anything that is not the plain passing shape — zero or several DKIM-Signature headers, non-ASCII
+// Several DKIM-Signature headers are accepted when every header before the first one of from_domain is a
+// well-formed signature of another domain (the reference skips those) and, with regex parts, only when the first
+// header is that candidate (the haystacks come from the first valid header); such a message is final on the device
+// only if the candidate verifies (FE_MULTI), otherwise the host front end takes it.
+// Anything that is not the plain passing shape — no DKIM-Signature header, non-ASCII
 // bytes in the signature header or a selected key, duplicate tags, i= q= x= l= tags, any validation
 // error, unknown c=/a=, domain mismatch, a header block not ending in CRLF CRLF, more than FE_MAXH
 // headers or FE_MAXN names in h=, an oversized preimage — sets FE_FALLBACK and the engine re-runs that
@@ -192,7 +196,7 @@ __device__ inline int fe_b64_decode(FeRd& R, uint32_t so, FeVal v, Sink sink) {
 
 // One message.  pre: the preimage slot (FE_PRE_CAP bytes); sigw: `limbs` words, zeroed here.
 __device__ inline void fe_process(const uint8_t* raw, uint32_t n, const uint8_t* dom, uint32_t dom_len, uint32_t k,
-                                  uint32_t limbs, uint8_t* pre, uint32_t* sigw, FeOut& out) {
+                                  uint32_t limbs, uint8_t* pre, uint32_t* sigw, FeOut& out, bool allow_skip = false) {
   out.flags = 0; out.body_off = 0; out.body_len = 0; out.pre_len = 0;
   for (int i = 0; i < 8; i++) out.bh[i] = 0;
   for (uint32_t i = 0; i < limbs; i++) sigw[i] = 0;
@@ -208,86 +212,106 @@ __device__ inline void fe_process(const uint8_t* raw, uint32_t n, const uint8_t*
     out.flags = FE_FALLBACK; return;
   }
   out.body_off = body_off; out.body_len = n - body_off;
-  // the single DKIM-Signature header
-  int sig_idx = -1;
+  // DKIM-Signature headers, top to bottom.  The reference walks them in order, skips those whose d= is another
+  // domain and lets the first one that verifies win (cfdkim::verify_email_with_key).  The device takes the first
+  // header of from_domain as its candidate, provided every header before it parses cleanly as a signature of another
+  // domain; a message with several signature headers is marked FE_MULTI so that a candidate that does NOT verify
+  // sends the message to the host front end (which tries the later headers and reports the reference's detail).
+  // With regex parts the haystacks come from the first VALID header whatever its domain, so skipping is off.
+  int sigs[8];
+  uint32_t n_sigs = 0;
   for (uint32_t i = 0; i < nh; i++) {
     const FeHdr& h = hs[i];
     bool is_sig = h.key_len == 14;
     const char* lit = "dkim-signature";
     for (uint32_t j = 0; is_sig && j < 14; j++) is_sig = fe_lower(R(h.key_off + j)) == (uint32_t)(uint8_t)lit[j];
-    if (is_sig) { if (sig_idx >= 0) { out.flags = FE_FALLBACK; return; } sig_idx = (int)i; }
+    if (is_sig) { if (n_sigs >= 8) { out.flags = FE_FALLBACK; return; } sigs[n_sigs++] = (int)i; }
+  }
+  if (n_sigs == 0) { out.flags = FE_FALLBACK; return; }
+  uint32_t so = 0, sn = 0;   // the candidate's header value is R(so .. so + sn)
+  FeVal tv, ta, tb, tbh, td, th, tc;
+  uint32_t seen = 0;  // bit per slot: v1 a2 b4 bh8 d16 h32 c64 s128
+  // 0: a well-formed rsa-sha256 signature of from_domain; 2: well-formed, another domain; 1: anything else
+  auto parse_sig = [&](int idx) -> int {
+    so = hs[idx].val_off;
+    sn = hs[idx].val_len;
+    for (uint32_t i = 0; i < sn; i++) if (R(so + i) & 0x80) return 1;
+    // ---- tag list (cfdkim parser.rs grammar): slots v a b bh d h c s; i q x l and duplicates fall back
+    tv.len = ta.len = tb.len = tbh.len = td.len = th.len = tc.len = 0;
+    tv.off = ta.off = tb.off = tbh.off = td.off = th.off = tc.off = 0;
+    seen = 0;
+    uint32_t pos = 0;
+    bool first = true;
+    for (;;) {
+      uint32_t p = pos;
+      if (!first) { if (p >= sn || R(so + p) != ';') break; p++; }
+      while (p < sn && fe_fws(R(so + p))) p++;
+      if (p >= sn || !fe_alpha(R(so + p))) { if (first) return 1; break; }
+      const uint32_t name_off = p;
+      while (p < sn && fe_alnum_(R(so + p))) p++;
+      const uint32_t name_len = p - name_off;
+      while (p < sn && fe_fws(R(so + p))) p++;
+      if (p >= sn || R(so + p) != '=') { if (first) return 1; break; }
+      p++;
+      while (p < sn && fe_fws(R(so + p))) p++;
+      FeVal val; val.off = p; val.len = 0;
+      if (p < sn && fe_valchar(R(so + p))) {
+        for (;;) {
+          while (p < sn && fe_valchar(R(so + p))) p++;
+          val.len = p - val.off;
+          uint32_t q = p;
+          while (q < sn && fe_fws(R(so + q))) q++;
+          if (q == p || q >= sn || !fe_valchar(R(so + q))) break;
+          p = q;
+        }
+      }
+      while (p < sn && fe_fws(R(so + p))) p++;
+      uint32_t bit = 0;
+      const uint32_t c0 = R(so + name_off), c1 = name_len > 1 ? R(so + name_off + 1) : 0;
+      if (name_len == 1) {
+        switch (c0) {
+          case 'v': bit = 1; tv = val; break;
+          case 'a': bit = 2; ta = val; break;
+          case 'b': bit = 4; tb = val; break;
+          case 'd': bit = 16; td = val; break;
+          case 'h': bit = 32; th = val; break;
+          case 'c': bit = 64; tc = val; break;
+          case 's': bit = 128; break;
+          case 'i': case 'q': case 'x': case 'l': return 1;
+          default: break;
+        }
+      } else if (name_len == 2 && c0 == 'b' && c1 == 'h') { bit = 8; tbh = val; }
+      if (bit) { if (seen & bit) return 1; seen |= bit; }
+      // unknown tag names may repeat in the reference's map without changing what it reads; names that
+      // collide with each other are irrelevant to verification, so they are ignored here
+      pos = p;
+      first = false;
+    }
+    // text the parser stopped at (a trailing ';', garbage) is ignored, as cfdkim's tag_list does
+    if ((seen & (1 | 2 | 4 | 8 | 16 | 32 | 128)) != (1 | 2 | 4 | 8 | 16 | 32 | 128)) return 1;
+    if (!fe_val_is(R, so, tv, "1") || !fe_val_is(R, so, ta, "rsa-sha256") || tb.len == 0) return 1;
+    // d= == from_domain (ASCII case-insensitive, FWS removed)
+    {
+      uint32_t j = 0;
+      bool ok = true;
+      for (uint32_t i = 0; i < td.len && ok; i++) {
+        const uint32_t c = R(so + td.off + i);
+        if (fe_fws(c)) continue;
+        ok = j < dom_len && fe_lower(c) == fe_lower(dom[j]);
+        j++;
+      }
+      if (!ok || j != dom_len) return 2;   // a signature of another domain: the reference skips it
+    }
+    return 0;
+  };
+  int sig_idx = -1;
+  for (uint32_t q = 0; q < n_sigs && sig_idx < 0; q++) {
+    const int r = parse_sig(sigs[q]);
+    if (r == 1 || (r == 2 && !allow_skip)) { out.flags = FE_FALLBACK; return; }
+    if (r == 0) sig_idx = sigs[q];
   }
   if (sig_idx < 0) { out.flags = FE_FALLBACK; return; }
-  const uint32_t so = hs[sig_idx].val_off;   // the signature header value is R(so .. so + sn)
-  const uint32_t sn = hs[sig_idx].val_len;
-  for (uint32_t i = 0; i < sn; i++) if (R(so + i) & 0x80) { out.flags = FE_FALLBACK; return; }
-  // ---- tag list (cfdkim parser.rs grammar): slots v a b bh d h c s; i q x l and duplicates fall back
-  FeVal tv, ta, tb, tbh, td, th, tc;
-  tv.len = ta.len = tb.len = tbh.len = td.len = th.len = tc.len = 0;
-  tv.off = ta.off = tb.off = tbh.off = td.off = th.off = tc.off = 0;
-  uint32_t seen = 0;  // bit per slot: v1 a2 b4 bh8 d16 h32 c64 s128
-  uint32_t pos = 0;
-  bool first = true;
-  for (;;) {
-    uint32_t p = pos;
-    if (!first) { if (p >= sn || R(so + p) != ';') break; p++; }
-    while (p < sn && fe_fws(R(so + p))) p++;
-    if (p >= sn || !fe_alpha(R(so + p))) { if (first) { out.flags = FE_FALLBACK; return; } break; }
-    const uint32_t name_off = p;
-    while (p < sn && fe_alnum_(R(so + p))) p++;
-    const uint32_t name_len = p - name_off;
-    while (p < sn && fe_fws(R(so + p))) p++;
-    if (p >= sn || R(so + p) != '=') { if (first) { out.flags = FE_FALLBACK; return; } break; }
-    p++;
-    while (p < sn && fe_fws(R(so + p))) p++;
-    FeVal val; val.off = p; val.len = 0;
-    if (p < sn && fe_valchar(R(so + p))) {
-      for (;;) {
-        while (p < sn && fe_valchar(R(so + p))) p++;
-        val.len = p - val.off;
-        uint32_t q = p;
-        while (q < sn && fe_fws(R(so + q))) q++;
-        if (q == p || q >= sn || !fe_valchar(R(so + q))) break;
-        p = q;
-      }
-    }
-    while (p < sn && fe_fws(R(so + p))) p++;
-    uint32_t bit = 0;
-    const uint32_t c0 = R(so + name_off), c1 = name_len > 1 ? R(so + name_off + 1) : 0;
-    if (name_len == 1) {
-      switch (c0) {
-        case 'v': bit = 1; tv = val; break;
-        case 'a': bit = 2; ta = val; break;
-        case 'b': bit = 4; tb = val; break;
-        case 'd': bit = 16; td = val; break;
-        case 'h': bit = 32; th = val; break;
-        case 'c': bit = 64; tc = val; break;
-        case 's': bit = 128; break;
-        case 'i': case 'q': case 'x': case 'l': out.flags = FE_FALLBACK; return;
-        default: break;
-      }
-    } else if (name_len == 2 && c0 == 'b' && c1 == 'h') { bit = 8; tbh = val; }
-    if (bit) { if (seen & bit) { out.flags = FE_FALLBACK; return; } seen |= bit; }
-    // unknown tag names may repeat in the reference's map without changing what it reads; names that
-    // collide with each other are irrelevant to verification, so they are ignored here
-    pos = p;
-    first = false;
-  }
-  // text the parser stopped at (a trailing ';', garbage) is ignored, as cfdkim's tag_list does
-  if ((seen & (1 | 2 | 4 | 8 | 16 | 32 | 128)) != (1 | 2 | 4 | 8 | 16 | 32 | 128)) { out.flags = FE_FALLBACK; return; }
-  if (!fe_val_is(R, so, tv, "1") || !fe_val_is(R, so, ta, "rsa-sha256") || tb.len == 0) { out.flags = FE_FALLBACK; return; }
-  // d= == from_domain (ASCII case-insensitive, FWS removed)
-  {
-    uint32_t j = 0;
-    bool ok = true;
-    for (uint32_t i = 0; i < td.len && ok; i++) {
-      const uint32_t c = R(so + td.off + i);
-      if (fe_fws(c)) continue;
-      ok = j < dom_len && fe_lower(c) == fe_lower(dom[j]);
-      j++;
-    }
-    if (!ok || j != dom_len) { out.flags = FE_FALLBACK; return; }
-  }
+  const uint32_t multi = n_sigs > 1 ? FE_MULTI : 0u;
   bool hr = false, br = false;
   if (seen & 64) {
     if (fe_val_is(R, so, tc, "relaxed/relaxed")) { hr = true; br = true; }
@@ -390,7 +414,7 @@ __device__ inline void fe_process(const uint8_t* raw, uint32_t n, const uint8_t*
   }
   if (overflow || o < 2) { out.flags = FE_FALLBACK; return; }
   out.pre_len = o - 2;  // final CRLF dropped
-  uint32_t flags = (hr ? FE_HDR_RELAXED : 0u) | (br ? FE_BODY_RELAXED : 0u);
+  uint32_t flags = (hr ? FE_HDR_RELAXED : 0u) | (br ? FE_BODY_RELAXED : 0u) | multi;
   // ---- bh= : 44 base64 characters -> 32 bytes -> 8 big-endian words
   {
     uint8_t bhb[48];
@@ -422,13 +446,13 @@ __device__ inline void fe_process(const uint8_t* raw, uint32_t n, const uint8_t*
 __global__ void __launch_bounds__(128)
 frontend_kernel(const uint8_t* __restrict__ span, const FeIn* __restrict__ in, uint32_t n, uint8_t* __restrict__ arena,
                 const uint64_t* __restrict__ msg_off, uint32_t* __restrict__ msg_len, uint32_t* __restrict__ sig_arena,
-                uint32_t* __restrict__ cand_bh, CanonItem* __restrict__ canon, FeOut* __restrict__ out) {
+                uint32_t* __restrict__ cand_bh, CanonItem* __restrict__ canon, FeOut* __restrict__ out, int allow_skip) {
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const FeIn fi = in[idx];
   FeOut fo;
   fe_process(span + fi.raw_off, fi.raw_len, arena + fi.dom_off, fi.dom_len, fi.k, fi.limbs, arena + msg_off[fi.pre_msg],
-             sig_arena + fi.sig_word_off, fo);
+             sig_arena + fi.sig_word_off, fo, allow_skip != 0);
   const bool live = (fo.flags & (FE_FALLBACK | FE_MAIL_PARSE)) == 0;
   msg_len[fi.pre_msg] = live ? fo.pre_len : 0u;
   CanonItem ci;
