@@ -261,7 +261,9 @@ _FE_B = st.sampled_from([b"QUJD\r\n\t REVG", b"QUJDREVG", b"QUJDRA==", b"QUJ", b
 @given(st.lists(st.tuples(_FE_NAME, _FE_SEP, _FE_VAL), min_size=1, max_size=7), _FE_BODY,
        st.sampled_from(["relaxed/relaxed", "simple/simple", "relaxed/simple", "simple/relaxed", "relaxed", "simple", "bogus", None]),
        st.lists(st.sampled_from(["from", "to", "subject", "date", "cc", "x-test", "From", "message-id", "missing", "subject "]), min_size=0, max_size=6),
-       st.sampled_from(["", " l=5;", " i=@example.com;", " x=99999999999;", " q=dns/txt;", " z=1;", " v=2;", " d=other.org;", " a=rsa-sha1;"]),
+       st.sampled_from(["", " l=5;", " i=@example.com;", " x=99999999999;", " q=dns/txt;", " z=1;", " v=2;", " d=other.org;", " a=rsa-sha1;",
+                        " i=user@sub.example.com; q=dns/txt; x=12345;", " i=@elsewhere.org;", " i=@Example.com;", " q=other;", " x=-5;", " x=1\r\n\t2;",
+                        " x=;", " i=;", " x=99999999999999999999;", " i=a@ex\r\n ample.com;"]),
        _FE_B, st.sampled_from(["top", "bottom", "both", "foreign", "foreign", "foreign_sha1", "foreign_after"]),
        st.sampled_from([b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA=", b"AAAA", b"AAAAAAAAAAAAAAAAAAAAAA\r\n\tAAAAAAAAAAAAAAAAAAAAA="]),
        st.booleans())
@@ -291,6 +293,17 @@ def test_device_front_end_source_on_dirty_mail(headers, body, canon, hnames, ext
     assert r >= 0, (r, raw)
     if where == "foreign_sha1" or (where == "foreign" and not allow_skip):
         assert r in (0, 2), (r, raw)
+
+
+def test_device_front_end_accepts_passing_optional_tags():
+    from zkemail_rs_b200 import synth
+    rng = np.random.default_rng(8)
+    k = key_pool()[2048][0]
+    cases = [(" i=@mail.example.com; q=dns/txt; x=9999999999;", 1), (" i=user@sub.mail.example.com;", 1), (" t=1700000000; x=1700000\r\n\t900;", 1),
+             (" i=@other.example.com;", 0), (" q=dns;", 0), (" x=0;", 1), (" x=abc;", 0), (" l=10;", 0)]
+    for extra, want in cases:
+        e = synth.make_email(rng, k, "mail.example.com", idx=3, body_len=200, extra_tags=extra)
+        assert _fe_compare(e.raw_email, b"mail.example.com") == want, extra
 
 
 def test_device_front_end_skips_foreign_signatures_only_when_allowed():

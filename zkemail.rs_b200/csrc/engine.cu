@@ -1014,7 +1014,8 @@ int launch_chunk(zkb_engine* e, const DeviceChunk& d, const zkb_regex_set* rs, c
   const bool pre = phase != 2, rsa = phase != 1;
   if (pre && d.n_fe) {
     // without regex parts, signature headers of other domains in front of the candidate may be skipped on the device
-    launch_frontend(d.raw_base, d.fe_in, d.n_fe, d.arena.p, d.msg_off, d.msg_len_rw, d.sig_rw, d.cand_bh_rw, d.canon_rw, d.fe_out, rs == nullptr, s);
+    launch_frontend(d.raw_base, d.fe_in, d.n_fe, d.arena.p, d.msg_off, d.msg_len_rw, d.sig_rw, d.cand_bh_rw, d.canon_rw, d.fe_out, rs == nullptr,
+                    (long long)(e->now_unix ? e->now_unix : (int64_t)time(nullptr)), s);
     nl++;
   }
   if (pre && d.n_canon) { launch_canon_body(d.raw_base, d.canon_items, d.n_canon, d.arena.p, d.msg_off, d.msg_len_rw, s); nl++; }

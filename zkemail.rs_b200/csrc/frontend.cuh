@@ -15,7 +15,7 @@
 // header is that candidate (the haystacks come from the first valid header); such a message is final on the device
 // only if the candidate verifies (FE_MULTI), otherwise the host front end takes it.
 // Anything that is not the plain passing shape — no DKIM-Signature header, non-ASCII
-// bytes in the signature header or a selected key, duplicate tags, i= q= x= l= tags, any validation
+// bytes in the signature header or a selected key, duplicate tags, an l= tag, i= / q= / x= tags that do not pass, any validation
 // error, unknown c=/a=, domain mismatch, a header block not ending in CRLF CRLF, more than FE_MAXH
 // headers or FE_MAXN names in h=, an oversized preimage — sets FE_FALLBACK and the engine re-runs that
 // message through the host front end, which implements every error path.  The device code therefore
@@ -196,7 +196,8 @@ __device__ inline int fe_b64_decode(FeRd& R, uint32_t so, FeVal v, Sink sink) {
 
 // One message.  pre: the preimage slot (FE_PRE_CAP bytes); sigw: `limbs` words, zeroed here.
 __device__ inline void fe_process(const uint8_t* raw, uint32_t n, const uint8_t* dom, uint32_t dom_len, uint32_t k,
-                                  uint32_t limbs, uint8_t* pre, uint32_t* sigw, FeOut& out, bool allow_skip = false) {
+                                  uint32_t limbs, uint8_t* pre, uint32_t* sigw, FeOut& out, bool allow_skip = false,
+                                  long long now = 0) {
   out.flags = 0; out.body_off = 0; out.body_len = 0; out.pre_len = 0;
   for (int i = 0; i < 8; i++) out.bh[i] = 0;
   for (uint32_t i = 0; i < limbs; i++) sigw[i] = 0;
@@ -229,16 +230,16 @@ __device__ inline void fe_process(const uint8_t* raw, uint32_t n, const uint8_t*
   }
   if (n_sigs == 0) { out.flags = FE_FALLBACK; return; }
   uint32_t so = 0, sn = 0;   // the candidate's header value is R(so .. so + sn)
-  FeVal tv, ta, tb, tbh, td, th, tc;
-  uint32_t seen = 0;  // bit per slot: v1 a2 b4 bh8 d16 h32 c64 s128
+  FeVal tv, ta, tb, tbh, td, th, tc, ti, tq, tx;
+  uint32_t seen = 0;  // bit per slot: v1 a2 b4 bh8 d16 h32 c64 s128 i256 q512 x1024
   // 0: a well-formed rsa-sha256 signature of from_domain; 2: well-formed, another domain; 1: anything else
   auto parse_sig = [&](int idx) -> int {
     so = hs[idx].val_off;
     sn = hs[idx].val_len;
     for (uint32_t i = 0; i < sn; i++) if (R(so + i) & 0x80) return 1;
     // ---- tag list (cfdkim parser.rs grammar): slots v a b bh d h c s; i q x l and duplicates fall back
-    tv.len = ta.len = tb.len = tbh.len = td.len = th.len = tc.len = 0;
-    tv.off = ta.off = tb.off = tbh.off = td.off = th.off = tc.off = 0;
+    tv.len = ta.len = tb.len = tbh.len = td.len = th.len = tc.len = ti.len = tq.len = tx.len = 0;
+    tv.off = ta.off = tb.off = tbh.off = td.off = th.off = tc.off = ti.off = tq.off = tx.off = 0;
     seen = 0;
     uint32_t pos = 0;
     bool first = true;
@@ -277,7 +278,10 @@ __device__ inline void fe_process(const uint8_t* raw, uint32_t n, const uint8_t*
           case 'h': bit = 32; th = val; break;
           case 'c': bit = 64; tc = val; break;
           case 's': bit = 128; break;
-          case 'i': case 'q': case 'x': case 'l': return 1;
+          case 'i': bit = 256; ti = val; break;
+          case 'q': bit = 512; tq = val; break;
+          case 'x': bit = 1024; tx = val; break;
+          case 'l': return 1;   // body length limits stay on the host path
           default: break;
         }
       } else if (name_len == 2 && c0 == 'b' && c1 == 'h') { bit = 8; tbh = val; }
@@ -290,6 +294,34 @@ __device__ inline void fe_process(const uint8_t* raw, uint32_t n, const uint8_t*
     // text the parser stopped at (a trailing ';', garbage) is ignored, as cfdkim's tag_list does
     if ((seen & (1 | 2 | 4 | 8 | 16 | 32 | 128)) != (1 | 2 | 4 | 8 | 16 | 32 | 128)) return 1;
     if (!fe_val_is(R, so, tv, "1") || !fe_val_is(R, so, ta, "rsa-sha256") || tb.len == 0) return 1;
+    // optional tags the validator looks at (cfdkim validate_header): accepted when they pass, host path when they
+    // do not (it reports the reference's error).  i= must end with the d= value (bytes, FWS removed); q= must be
+    // dns/txt; x= must be a plain decimal clearly in the future of `now` (a signature near its expiry is left to the
+    // host's own clock).
+    if (seen & 256) {
+      uint32_t li = 0, ld = 0;
+      for (uint32_t i = 0; i < ti.len; i++) if (!fe_fws(R(so + ti.off + i))) li++;
+      for (uint32_t i = 0; i < td.len; i++) if (!fe_fws(R(so + td.off + i))) ld++;
+      if (li < ld) return 1;
+      uint32_t a = ti.len, b = td.len;
+      for (uint32_t m = 0; m < ld; m++) {
+        do { a--; } while (fe_fws(R(so + ti.off + a)));
+        do { b--; } while (fe_fws(R(so + td.off + b)));
+        if (R(so + ti.off + a) != R(so + td.off + b)) return 1;
+      }
+    }
+    if ((seen & 512) && !fe_val_is(R, so, tq, "dns/txt")) return 1;
+    if (seen & 1024) {
+      long long x = 0;
+      uint32_t digits = 0;
+      for (uint32_t i = 0; i < tx.len; i++) {
+        const uint32_t c = R(so + tx.off + i);
+        if (fe_fws(c)) continue;
+        if (c < '0' || c > '9' || ++digits > 17) return 1;
+        x = x * 10 + (long long)(c - '0');
+      }
+      if (digits == 0 || now + 2 > x + 15 * 60) return 1;
+    }
     // d= == from_domain (ASCII case-insensitive, FWS removed)
     {
       uint32_t j = 0;
@@ -446,13 +478,14 @@ __device__ inline void fe_process(const uint8_t* raw, uint32_t n, const uint8_t*
 __global__ void __launch_bounds__(128)
 frontend_kernel(const uint8_t* __restrict__ span, const FeIn* __restrict__ in, uint32_t n, uint8_t* __restrict__ arena,
                 const uint64_t* __restrict__ msg_off, uint32_t* __restrict__ msg_len, uint32_t* __restrict__ sig_arena,
-                uint32_t* __restrict__ cand_bh, CanonItem* __restrict__ canon, FeOut* __restrict__ out, int allow_skip) {
+                uint32_t* __restrict__ cand_bh, CanonItem* __restrict__ canon, FeOut* __restrict__ out, int allow_skip,
+                long long now) {
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const FeIn fi = in[idx];
   FeOut fo;
   fe_process(span + fi.raw_off, fi.raw_len, arena + fi.dom_off, fi.dom_len, fi.k, fi.limbs, arena + msg_off[fi.pre_msg],
-             sig_arena + fi.sig_word_off, fo, allow_skip != 0);
+             sig_arena + fi.sig_word_off, fo, allow_skip != 0, now);
   const bool live = (fo.flags & (FE_FALLBACK | FE_MAIL_PARSE)) == 0;
   msg_len[fi.pre_msg] = live ? fo.pre_len : 0u;
   CanonItem ci;

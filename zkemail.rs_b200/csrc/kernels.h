@@ -31,7 +31,7 @@ void launch_dfa_strided(uint32_t elem, bool direct, const uint8_t* arena, const 
 void launch_canon_body(const uint8_t* span, const CanonItem* items, uint32_t n, uint8_t* arena, const uint64_t* msg_off,
                        uint32_t* msg_len, cudaStream_t s);
 void launch_frontend(const uint8_t* span, const FeIn* in, uint32_t n, uint8_t* arena, const uint64_t* msg_off, uint32_t* msg_len,
-                     uint32_t* sig_arena, uint32_t* cand_bh, CanonItem* canon, FeOut* out, bool allow_skip, cudaStream_t s);
+                     uint32_t* sig_arena, uint32_t* cand_bh, CanonItem* canon, FeOut* out, bool allow_skip, long long now, cudaStream_t s);
 void launch_int_peak(int kind, unsigned grid, unsigned block, uint32_t* out, uint32_t seed, int iters, cudaStream_t s);
 
 }  // namespace zkb
