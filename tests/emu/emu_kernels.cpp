@@ -146,7 +146,8 @@ int emu_fe_compare(const uint8_t* raw_in, uint32_t n, const uint8_t* dom, uint32
   std::vector<uint8_t> pre(FE_PRE_CAP + 64, 0xEE);
   std::vector<uint32_t> sigw(limbs, 0xDEADBEEFu);
   FeOut fo;
-  fe_process(raw, n, dom, dom_len, k, limbs, pre.data(), sigw.data(), fo, allow_skip != 0, 1);
+  uint32_t body_l = 0;
+  fe_process(raw, n, dom, dom_len, k, limbs, pre.data(), sigw.data(), fo, body_l, allow_skip != 0, 1);
   std::vector<HeaderField> hs;
   size_t body_off = 0;
   const bool parsed = parse_headers(raw, n, hs, body_off);
@@ -174,7 +175,13 @@ int emu_fe_compare(const uint8_t* raw_in, uint32_t n, const uint8_t* dom, uint32
   bool hr, br;
   if (!parse_canon_tag(sig, hr, br)) return -6;
   if (!sig.val_is(sig.get("a"), "rsa-sha256")) return -7;
-  if (sig.get("l")) return -8;
+  {
+    uint64_t l = 0;
+    const Tag* tl = sig.get("l");
+    if (tl && !parse_usize_tag(sig, tl, l)) return -8;   // the device must have declined an l= the reference rejects
+    if ((tl != nullptr) != ((fo.flags & FE_HAS_L) != 0)) return -19;
+    if (tl && body_l != (l > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)l)) return -20;
+  }
   if (hr != ((fo.flags & FE_HDR_RELAXED) != 0) || br != ((fo.flags & FE_BODY_RELAXED) != 0)) return -9;
   size_t bl = 0;
   const uint8_t* b = find_body(raw, n, bl, body_off);

@@ -300,7 +300,8 @@ def test_device_front_end_accepts_passing_optional_tags():
     rng = np.random.default_rng(8)
     k = key_pool()[2048][0]
     cases = [(" i=@mail.example.com; q=dns/txt; x=9999999999;", 1), (" i=user@sub.mail.example.com;", 1), (" t=1700000000; x=1700000\r\n\t900;", 1),
-             (" i=@other.example.com;", 0), (" q=dns;", 0), (" x=0;", 1), (" x=abc;", 0), (" l=10;", 0)]
+             (" i=@other.example.com;", 0), (" q=dns;", 0), (" x=0;", 1), (" x=abc;", 0), (" l=10;", 1), (" l=+7;", 1), (" l=0;", 1),
+             (" l=99999999999;", 1), (" l=;", 0), (" l=1a;", 0), (" l=-1;", 0)]
     for extra, want in cases:
         e = synth.make_email(rng, k, "mail.example.com", idx=3, body_len=200, extra_tags=extra)
         assert _fe_compare(e.raw_email, b"mail.example.com") == want, extra

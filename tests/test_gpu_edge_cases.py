@@ -90,6 +90,24 @@ def test_l_tag_and_truncated_body(engine):
     e2 = z.Email("l.example.com", raw.replace(b" l=100;", b" l=99;"), z.PublicKey(k.der, "rsa"))
     got = _check(engine, [e1, e2])
     assert int(got[0]["status"]) == 0 and int(got[1]["status"]) == 3
+    # regex parts see the TRUNCATED canonical body (the appended text is not part of the haystack), captures included
+    from tests.util import contiguous_views
+    body3 = b"Transaction ID: ZX81\r\n" + b"a" * 36 + b"\r\n" + b"b" * 38 + b"\r\n"
+    raw3 = synth.sign_email(headers, body3, k, "l.example.com", extra_tags=" l=100;")
+    e3 = z.Email("l.example.com", raw3 + b"Transaction ID: LATE99 appended after signing\r\n", z.PublicKey(k.der, "rsa"))
+    for pat, caps, want in ((r"Transaction ID: [A-Z0-9]+", ["ZX81"], 0), (r"Transaction ID: [A-Z0-9]+", ["LATE99"], 7), (r"appended", None, 7)):
+        info = RegexInfo(None, [CompiledRegex(z.compile_regex(pat), caps)])
+        ex = oracle.verify_batch([e3], None, info.body_parts, now=NOW)
+        g = engine.verify_with_regex_batch([e3], info)
+        assert_records_equal(g[0], ex[0], (pat, caps))
+        assert int(g[0]["status"]) == want, (pat, caps)
+        buf, views = contiguous_views([e3])
+        engine.register_host(buf)
+        try:
+            rs = z.RegexSet(engine, info)
+            assert_records_equal(engine.verify_views(views, rs)[0], ex[0], ("registered", pat, caps))
+        finally:
+            engine.unregister_host(buf)
 
 
 def test_multiple_signatures(engine):

@@ -61,7 +61,8 @@ struct __align__(16) CanonItem {
 
 enum { FE_FALLBACK = 1u, FE_MAIL_PARSE = 2u, FE_BH_VALID = 4u, FE_SIG_SYNTAX = 8u, FE_SIG_BADLEN = 16u,
        FE_HDR_RELAXED = 32u, FE_BODY_RELAXED = 64u,
-       FE_MULTI = 128u /* several DKIM-Signature headers: a candidate that fails goes to the host front end */ };
+       FE_MULTI = 128u /* several DKIM-Signature headers: a candidate that fails goes to the host front end */,
+       FE_HAS_L = 256u /* l= present: the canonical body is truncated (CanonItem.l) */ };
 
 struct __align__(16) FeIn {   // host-built, one per message
   uint64_t raw_off;           // message bytes in the raw span buffer

@@ -1223,7 +1223,7 @@ bool resolve_email_fe(const zkb_engine* e, const Chunk& ch, size_t i, const uint
         if (ec.caps[q].part != p) continue;
         if (!loaded) {  // rebuild the haystack on the host from the raw message (only emails with captures pay)
           HayView hv;
-          if (body) {
+          if (body && !(fo.flags & FE_HAS_L)) {
             scratch.resize((size_t)fo.body_len + 64);
             size_t cl = (fo.flags & FE_BODY_RELAXED) ? canon_body_relaxed(raw + fo.body_off, fo.body_len, scratch.data())
                                                      : canon_body_simple(raw + fo.body_off, fo.body_len, scratch.data());
@@ -1233,9 +1233,10 @@ bool resolve_email_fe(const zkb_engine* e, const Chunk& ch, size_t i, const uint
             size_t hl = 0, bl = 0;
             int detail2 = 0;
             if (zkb_host_canonicalize(raw, view.raw_email_len, e->now_unix, &hp, &hl, &bp, &bl, &detail2) != ZKB_OK) { ok = false; break; }
-            scratch.assign(hp, hp + hl);
+            if (body) scratch.assign(bp, bp + bl);   // l= bodies: the host canonicaliser applies the truncation
+            else scratch.assign(hp, hp + hl);
             free(hp); free(bp);
-            hv.p = scratch.data(); hv.n = (uint32_t)hl;
+            hv.p = scratch.data(); hv.n = (uint32_t)scratch.size();
           }
           cleaned_span(hv, body, r.y, r.z, s1);
           bool ascii = true;

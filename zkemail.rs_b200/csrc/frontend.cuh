@@ -15,7 +15,7 @@
 // header is that candidate (the haystacks come from the first valid header); such a message is final on the device
 // only if the candidate verifies (FE_MULTI), otherwise the host front end takes it.
 // Anything that is not the plain passing shape — no DKIM-Signature header, non-ASCII
-// bytes in the signature header or a selected key, duplicate tags, an l= tag, i= / q= / x= tags that do not pass, any validation
+// bytes in the signature header or a selected key, duplicate tags, i= / q= / x= / l= tags that do not pass, any validation
 // error, unknown c=/a=, domain mismatch, a header block not ending in CRLF CRLF, more than FE_MAXH
 // headers or FE_MAXN names in h=, an oversized preimage — sets FE_FALLBACK and the engine re-runs that
 // message through the host front end, which implements every error path.  The device code therefore
@@ -196,8 +196,9 @@ __device__ inline int fe_b64_decode(FeRd& R, uint32_t so, FeVal v, Sink sink) {
 
 // One message.  pre: the preimage slot (FE_PRE_CAP bytes); sigw: `limbs` words, zeroed here.
 __device__ inline void fe_process(const uint8_t* raw, uint32_t n, const uint8_t* dom, uint32_t dom_len, uint32_t k,
-                                  uint32_t limbs, uint8_t* pre, uint32_t* sigw, FeOut& out, bool allow_skip = false,
-                                  long long now = 0) {
+                                  uint32_t limbs, uint8_t* pre, uint32_t* sigw, FeOut& out, uint32_t& body_l,
+                                  bool allow_skip = false, long long now = 0) {
+  body_l = 0;
   out.flags = 0; out.body_off = 0; out.body_len = 0; out.pre_len = 0;
   for (int i = 0; i < 8; i++) out.bh[i] = 0;
   for (uint32_t i = 0; i < limbs; i++) sigw[i] = 0;
@@ -230,16 +231,16 @@ __device__ inline void fe_process(const uint8_t* raw, uint32_t n, const uint8_t*
   }
   if (n_sigs == 0) { out.flags = FE_FALLBACK; return; }
   uint32_t so = 0, sn = 0;   // the candidate's header value is R(so .. so + sn)
-  FeVal tv, ta, tb, tbh, td, th, tc, ti, tq, tx;
-  uint32_t seen = 0;  // bit per slot: v1 a2 b4 bh8 d16 h32 c64 s128 i256 q512 x1024
+  FeVal tv, ta, tb, tbh, td, th, tc, ti, tq, tx, tl;
+  uint32_t seen = 0;  // bit per slot: v1 a2 b4 bh8 d16 h32 c64 s128 i256 q512 x1024 l2048
   // 0: a well-formed rsa-sha256 signature of from_domain; 2: well-formed, another domain; 1: anything else
   auto parse_sig = [&](int idx) -> int {
     so = hs[idx].val_off;
     sn = hs[idx].val_len;
     for (uint32_t i = 0; i < sn; i++) if (R(so + i) & 0x80) return 1;
     // ---- tag list (cfdkim parser.rs grammar): slots v a b bh d h c s; i q x l and duplicates fall back
-    tv.len = ta.len = tb.len = tbh.len = td.len = th.len = tc.len = ti.len = tq.len = tx.len = 0;
-    tv.off = ta.off = tb.off = tbh.off = td.off = th.off = tc.off = ti.off = tq.off = tx.off = 0;
+    tv.len = ta.len = tb.len = tbh.len = td.len = th.len = tc.len = ti.len = tq.len = tx.len = tl.len = 0;
+    tv.off = ta.off = tb.off = tbh.off = td.off = th.off = tc.off = ti.off = tq.off = tx.off = tl.off = 0;
     seen = 0;
     uint32_t pos = 0;
     bool first = true;
@@ -281,7 +282,7 @@ __device__ inline void fe_process(const uint8_t* raw, uint32_t n, const uint8_t*
           case 'i': bit = 256; ti = val; break;
           case 'q': bit = 512; tq = val; break;
           case 'x': bit = 1024; tx = val; break;
-          case 'l': return 1;   // body length limits stay on the host path
+          case 'l': bit = 2048; tl = val; break;
           default: break;
         }
       } else if (name_len == 2 && c0 == 'b' && c1 == 'h') { bit = 8; tbh = val; }
@@ -322,6 +323,19 @@ __device__ inline void fe_process(const uint8_t* raw, uint32_t n, const uint8_t*
       }
       if (digits == 0 || now + 2 > x + 15 * 60) return 1;
     }
+    if (seen & 2048) {   // l=: [+]digits (cfdkim parses a usize); values beyond 32 bits never truncate a body that fits
+      uint32_t digits = 0, lead = 0;
+      unsigned long long v = 0;
+      for (uint32_t i = 0; i < tl.len; i++) {
+        const uint32_t c = R(so + tl.off + i);
+        if (fe_fws(c)) continue;
+        if (c == '+' && digits == 0 && lead == 0) { lead = 1; continue; }
+        if (c < '0' || c > '9' || ++digits > 18) return 1;
+        v = v * 10 + (unsigned long long)(c - '0');
+      }
+      if (digits == 0) return 1;
+      body_l = v > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)v;
+    }
     // d= == from_domain (ASCII case-insensitive, FWS removed)
     {
       uint32_t j = 0;
@@ -343,7 +357,7 @@ __device__ inline void fe_process(const uint8_t* raw, uint32_t n, const uint8_t*
     if (r == 0) sig_idx = sigs[q];
   }
   if (sig_idx < 0) { out.flags = FE_FALLBACK; return; }
-  const uint32_t multi = n_sigs > 1 ? FE_MULTI : 0u;
+  const uint32_t multi = (n_sigs > 1 ? FE_MULTI : 0u) | ((seen & 2048) ? FE_HAS_L : 0u);
   bool hr = false, br = false;
   if (seen & 64) {
     if (fe_val_is(R, so, tc, "relaxed/relaxed")) { hr = true; br = true; }
@@ -484,16 +498,17 @@ frontend_kernel(const uint8_t* __restrict__ span, const FeIn* __restrict__ in, u
   if (idx >= n) return;
   const FeIn fi = in[idx];
   FeOut fo;
+  uint32_t body_l = 0;
   fe_process(span + fi.raw_off, fi.raw_len, arena + fi.dom_off, fi.dom_len, fi.k, fi.limbs, arena + msg_off[fi.pre_msg],
-             sig_arena + fi.sig_word_off, fo, allow_skip != 0, now);
+             sig_arena + fi.sig_word_off, fo, body_l, allow_skip != 0, now);
   const bool live = (fo.flags & (FE_FALLBACK | FE_MAIL_PARSE)) == 0;
   msg_len[fi.pre_msg] = live ? fo.pre_len : 0u;
   CanonItem ci;
   ci.raw_off = fi.raw_off + fo.body_off;
   ci.raw_len = live ? fo.body_len : 0u;
   ci.msg = fi.body_msg;
-  ci.flags = (fo.flags & FE_BODY_RELAXED) ? 1u : 0u;
-  ci.l = 0; ci.pad[0] = ci.pad[1] = 0;
+  ci.flags = ((fo.flags & FE_BODY_RELAXED) ? 1u : 0u) | ((fo.flags & FE_HAS_L) ? 2u : 0u);
+  ci.l = body_l; ci.pad[0] = ci.pad[1] = 0;
   canon[idx] = ci;
   for (int i = 0; i < 8; i++) cand_bh[(size_t)fi.cand * 8 + i] = fo.bh[i];
   out[idx] = fo;
