@@ -87,8 +87,8 @@ inline bool ieq_ascii(const uint8_t* a, size_t al, const char* b, size_t bl) {
   if (al != bl) return false;
   for (size_t i = 0; i < al; i++) {
     uint8_t x = a[i], y = (uint8_t)b[i];
-    if (x - 'A' < 26u) x += 32;
-    if (y - 'A' < 26u) y += 32;
+    if ((unsigned)(x - 'A') < 26u) x += 32;
+    if ((unsigned)(y - 'A') < 26u) y += 32;
     if (x != y) return false;
   }
   return true;

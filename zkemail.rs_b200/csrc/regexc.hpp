@@ -318,7 +318,7 @@ struct Parser {
     if (atom < 0) return -1;
     for (;;) {
       if (pos >= n) break;
-      uint32_t mn, mx;
+      uint32_t mn = 0, mx = 0;
       uint8_t c = p[pos];
       if (c == '*') { mn = 0; mx = INF; pos++; }
       else if (c == '+') { mn = 1; mx = INF; pos++; }
