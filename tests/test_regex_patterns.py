@@ -38,3 +38,33 @@ def test_compiler_oracle_and_kernel_source_agree_with_python_re():
             assert int(row[0]) == cnt, (pat, hay)
             if cnt:
                 assert (int(row[1]), int(row[2])) == want[0], (pat, hay)
+
+
+def test_ascii_word_boundaries():
+    r"""(?-u:\b) / (?-u:\B) compile (one "previous byte was a word byte" bit per DFA state) and agree with Python's
+    bytes-mode \b; Unicode \b is rejected like DFARegex::new rejects it (helpers/src/regex.rs:20 would return Err)."""
+    cases = [(r"(?-u:\b)foo(?-u:\b)", rb"\bfoo\b"), (r"(?-u)\bfoo\b", rb"\bfoo\b"), (r"(?-u:\B)oo", rb"\Boo"), (r"(?-u)\b[a-z]+\b", rb"\b[a-z]+\b"),
+             (r"(?-u)\b\d+\b", rb"\b\d+\b"), (r"(?-u)x\b", rb"x\b"), (r"(?-u)\bx", rb"\bx"), (r"(?-u)a\Bb", rb"a\Bb"),
+             (r"(?-u)\b(cat|dog)s?\b", rb"\b(cat|dog)s?\b"), (r"(?i-u)\bID: [a-z0-9]+\b", rb"(?i)\bID: [a-z0-9]+\b"), (r"(?m-u)^\w+\b", rb"(?m)^\w+\b")]
+    hays = [b"foo", b" foo ", b"foofoo foo_foo foo-foo", b"a foo\xc3\xa9 foo", b"", b"x", b"xx x.x ax xa", b"ab a b", b"cats dog dogs cat. catsup",
+            b"id: a1 ID: zz9_ ID: Q ", b"12 a12 12a 3", b"the cat sat on the mat", b"\nfoo\n", b"foo\xff", b"one\ntwo three\nfour"]
+    for pat, py in cases:
+        d = z.compile_regex(pat)
+        rows = np.asarray(emu.dfa_scan(d.fwd, d.bwd, hays))
+        for hay, row in zip(hays, rows):
+            want = [(m.start(), m.end()) for m in re.finditer(py, hay)]
+            cnt, spans = oracle.dfa_find_iter(d.fwd, d.bwd, hay)
+            assert [tuple(s) for s in spans[:cnt]] == want, (pat, hay)
+            assert int(row[0]) == cnt and (not cnt or (int(row[1]), int(row[2])) == want[0]), (pat, hay)
+    # patterns that match the empty string: Rust's iteration rule, kernel source against the oracle
+    for pat in (r"(?-u)\b", r"(?-u)\B", r"(?-u)\b|x"):
+        d = z.compile_regex(pat)
+        for hay, row in zip(hays, np.asarray(emu.dfa_scan(d.fwd, d.bwd, hays))):
+            cnt, spans = oracle.dfa_find_iter(d.fwd, d.bwd, hay)
+            assert int(row[0]) == cnt and (not cnt or (int(row[1]), int(row[2])) == tuple(spans[0])), (pat, hay)
+    d = z.compile_regex(r"(?-u)\b")
+    assert [tuple(s) for s in oracle.dfa_find_iter(d.fwd, d.bwd, b"ab cd")[1][:4]] == [(0, 0), (2, 2), (3, 3), (5, 5)]
+    import pytest
+    for pat in (r"\bfoo", r"(?u)\bx", r"[\b]"):
+        with pytest.raises(z.RegexError):
+            z.compile_regex(pat)

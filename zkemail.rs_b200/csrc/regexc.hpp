@@ -15,7 +15,9 @@
 // punctuation), `.`, classes with ranges / negation / POSIX names / nested \d \w \s, \d \w \s \D \W \S
 // (Unicode definitions in (?u) mode from generated tables, ASCII under (?-u)), groups (capturing, non-capturing,
 // named), alternation, greedy and lazy * + ? {m} {m,} {m,n}, anchors ^ $ \A \z, flags i m s U u.
-// Rejected (ZKB_E_REGEX): look-around other than anchors (\b \B), Unicode property classes (\p),
+// ASCII word boundaries ((?-u:\b), (?-u:\B)) are resolved by the determiniser (one "previous byte was a word byte"
+// bit per state, as regex-automata does).
+// Rejected (ZKB_E_REGEX): Unicode word boundaries (no dense DFA exists for them), Unicode property classes (\p),
 // class set operations, back-references, the x flag.
 #pragma once
 #include <stdint.h>
@@ -36,7 +38,9 @@ namespace rx {
 typedef std::pair<uint32_t, uint32_t> Range;  // inclusive
 typedef std::vector<Range> RangeSet;
 
-enum Look { LOOK_START_TEXT = 1, LOOK_END_TEXT = 2, LOOK_START_LINE = 4, LOOK_END_LINE = 8 };
+enum Look { LOOK_START_TEXT = 1, LOOK_END_TEXT = 2, LOOK_START_LINE = 4, LOOK_END_LINE = 8,
+            LOOK_WORD_ASCII = 16, LOOK_NOT_WORD_ASCII = 32 };   // (?-u:\b) (?-u:\B)
+inline bool is_word_byte(int b) { return (b >= '0' && b <= '9') || (b >= 'A' && b <= 'Z') || (b >= 'a' && b <= 'z') || b == '_'; }
 
 inline void normalize(RangeSet& r) {
   std::sort(r.begin(), r.end());
@@ -214,6 +218,13 @@ struct Parser {
       case 'd': case 'D': case 'w': case 'W': case 's': case 'S': perl_class(e, cls, neg, cur_unicode); return 1;
       case 'A': if (in_class) break; look = LOOK_START_TEXT; return 2;
       case 'z': if (in_class) break; look = LOOK_END_TEXT; return 2;
+      case 'b': case 'B':
+        if (in_class) break;
+        // DFARegex::new cannot build a dense DFA with Unicode word boundaries either (helpers/src/regex.rs:20 would
+        // return Err); the ASCII ones are look-arounds the determiniser resolves with one bit of state
+        if (cur_unicode) { fail("Unicode word boundary cannot be compiled to a DFA; write (?-u:\\b)"); return -1; }
+        look = e == 'b' ? LOOK_WORD_ASCII : LOOK_NOT_WORD_ASCII;
+        return 2;
       default: break;
     }
     if (e < 0x80 && !((e >= '0' && e <= '9') || ((e | 32) >= 'a' && (e | 32) <= 'z')) && e != '<' && e != '>') {
@@ -560,7 +571,8 @@ struct NfaBuilder {
       case Node::EMPTY: return next;
       case Node::LOOK: {
         int lk = nd.look;
-        if (reverse) lk = lk == LOOK_START_TEXT ? LOOK_END_TEXT : lk == LOOK_END_TEXT ? LOOK_START_TEXT : lk == LOOK_START_LINE ? LOOK_END_LINE : LOOK_START_LINE;
+        if (reverse && !(lk & (LOOK_WORD_ASCII | LOOK_NOT_WORD_ASCII)))   // word boundaries read the same in both directions
+          lk = lk == LOOK_START_TEXT ? LOOK_END_TEXT : lk == LOOK_END_TEXT ? LOOK_START_TEXT : lk == LOOK_START_LINE ? LOOK_END_LINE : LOOK_START_LINE;
         NState s; s.t = NState::LOOKS; s.look = lk; s.next = next;
         nfa.looks_any |= lk;
         return nfa.add(s);
@@ -621,6 +633,7 @@ struct DState {
   std::vector<int> ids;  // NFA states (RANGE / LOOKS / MATCH) in priority order
   int look_have = 0, look_need = 0;
   bool is_match = false;
+  bool from_word = false;   // the byte that led here is an ASCII word byte (tracked only for patterns with \b / \B)
 };
 struct Dfa {
   uint32_t n_classes = 0;  // including EOI
@@ -668,7 +681,8 @@ struct Determinizer {
     if (!d.look_need) d.look_have = 0;
     std::vector<int> key;
     key.reserve(d.ids.size() + 2);
-    key.push_back(d.is_match ? 1 : 0);
+    if (!(nfa.looks_any & (LOOK_WORD_ASCII | LOOK_NOT_WORD_ASCII))) d.from_word = false;
+    key.push_back((d.is_match ? 1 : 0) | (d.from_word ? 2 : 0));
     key.push_back(d.look_have);
     key.insert(key.end(), d.ids.begin(), d.ids.end());
     auto it = index.find(key);
@@ -678,9 +692,10 @@ struct Determinizer {
     index.emplace(std::move(key), id);
     return id;
   }
-  uint32_t start_state(int nfa_start, int look_have) {
+  uint32_t start_state(int nfa_start, int look_have, bool from_word) {
     DState d;
     d.look_have = look_have;
+    d.from_word = from_word;
     epoch++;
     closure(nfa_start, look_have, d.ids);
     return intern(d);
@@ -693,6 +708,8 @@ struct Determinizer {
       int have = src.look_have;
       if (unit == 256) have |= LOOK_END_TEXT | LOOK_END_LINE;
       if (unit == '\n') have |= LOOK_END_LINE;
+      if (nfa.looks_any & (LOOK_WORD_ASCII | LOOK_NOT_WORD_ASCII))   // between the byte behind and the byte ahead (EOI: not a word byte)
+        have |= (src.from_word != (unit < 256 && is_word_byte(unit))) ? LOOK_WORD_ASCII : LOOK_NOT_WORD_ASCII;
       if ((have & ~src.look_have) & src.look_need) {
         std::vector<int> re;
         epoch++;
@@ -701,6 +718,7 @@ struct Determinizer {
       }
     }
     DState d;
+    d.from_word = unit < 256 && is_word_byte(unit);
     if ((nfa.looks_any & (LOOK_START_LINE | LOOK_END_LINE)) && unit == '\n') d.look_have |= LOOK_START_LINE;
     epoch++;
     for (int id : cur) {
@@ -724,6 +742,8 @@ inline bool determinize(const Nfa& nfa, bool leftmost_first, bool with_unanchore
   for (auto& s : nfa.st)
     if (s.t == NState::RANGE) { bound[s.lo] = true; bound[(int)s.hi + 1] = true; }
   if (nfa.looks_any & (LOOK_START_LINE | LOOK_END_LINE)) { bound['\n'] = true; bound['\n' + 1] = true; }
+  if (nfa.looks_any & (LOOK_WORD_ASCII | LOOK_NOT_WORD_ASCII))
+    for (int b = 1; b <= 256; b++) if (is_word_byte(b - 1) != (b < 256 && is_word_byte(b))) bound[b] = true;
   std::vector<int> rep;
   int cls = -1;
   for (int b = 0; b < 256; b++) {
@@ -738,8 +758,8 @@ inline bool determinize(const Nfa& nfa, bool leftmost_first, bool with_unanchore
   // start kinds: NonWordByte, WordByte, Text, LineLF, LineCR, CustomLineTerminator
   static const int KIND_LOOK[6] = {0, 0, LOOK_START_TEXT | LOOK_START_LINE, LOOK_START_LINE, 0, 0};
   for (int k = 0; k < 6; k++) {
-    uint32_t a = det.start_state(nfa.start_anchored, KIND_LOOK[k]);
-    uint32_t u = with_unanchored ? det.start_state(nfa.start_unanchored, KIND_LOOK[k]) : a;
+    uint32_t a = det.start_state(nfa.start_anchored, KIND_LOOK[k], k == 1);
+    uint32_t u = with_unanchored ? det.start_state(nfa.start_unanchored, KIND_LOOK[k], k == 1) : a;
     out.start[k] = u;
     out.start[6 + k] = a;
   }
