@@ -68,3 +68,14 @@ def test_ascii_word_boundaries():
     for pat in (r"\bfoo", r"(?u)\bx", r"[\b]"):
         with pytest.raises(z.RegexError):
             z.compile_regex(pat)
+
+
+def test_capture_resolution_accepts_rust_flag_groups():
+    """compile_regex_parts (helpers/src/regex.rs:16-51) resolves capture strings with Python `re`; Rust's `u` flag
+    spellings must not trip it."""
+    from zkemail_rs_b200.structs import RegexPattern
+    hay = b"x ID: abc9 y\r\nsubject:Hi there\r\n"
+    for pat, want in ((r"(?-u:\b)ID: ([a-z0-9]+)", ["abc9"]), (r"(?-u)\bID: ([a-z0-9]+)\b", ["abc9"]), (r"(?i-u)\bid: ([a-z0-9]+)", ["abc9"]),
+                      (r"(?u)subject:(\w+) (\w+)", ["Hi", "there"]), (r"(?<n>ID): (\w+)", ["ID", "abc9"])):
+        idx = list(range(1, len(want) + 1))
+        assert z.compile_regex_parts([RegexPattern(pat, idx)], hay)[0].captures == want, pat

@@ -249,6 +249,18 @@ def _py_pattern(pattern: str) -> bytes:
     for k, v in posix.items():
         p = p.replace(f"[:{k}:]", v)
     p = p.replace(r"\z", r"\Z").replace("(?<", "(?P<") if "(?<=" not in p and "(?<!" not in p else p
+
+    # inline flag groups: Python's bytes patterns are ASCII-only and have no `u` flag to set or clear
+    def _flags(m):
+        on, off, tail = m.group(1), (m.group(2) or "")[1:], m.group(3)
+        on, off = on.replace("u", ""), off.replace("u", "")
+        if "U" in on or "U" in off:
+            raise RegexError("the swap-greed flag U has no Python equivalent (capture resolution)")
+        body = on + ("-" + off if off else "")
+        if not body:
+            return "(?:" if tail == ":" else ""
+        return "(?" + body + tail
+    p = re.sub(r"\(\?([a-zA-Z]*)(-[a-zA-Z]*)?([:)])", _flags, p)
     return p.encode("utf-8")
 
 
