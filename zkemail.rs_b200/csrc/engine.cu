@@ -1646,6 +1646,7 @@ int zkb_batch_prepare(zkb_engine* e, const zkb_email_view* emails, size_t n, con
 int zkb_batch_run_async(zkb_batch* b) {
   if (!b) return ZKB_E_INVALID;
   zkb_engine* e = b->eng;
+  std::lock_guard<std::mutex> lock(e->run_mu);   // enqueue only; serialised with the other calls on this engine
   CK(cudaSetDevice(e->device));
   cudaStream_t s = e->slots[0].stream;
   const size_t nc = b->dev.size();
