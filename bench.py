@@ -301,17 +301,12 @@ def main():
         if gather is not None:
             gather()
 
-    # warm-up: at least W (>= 3) steps and at least ~0.4 s of device work, so that a fresh box has left its idle power
-    # state before the timed region (a 23.2 ms first step-set was seen once against the usual 22.6 ms)
-    n_warm = max(W, 3)
+    # warm-up: W (>= 3) steps plus a fixed 15 more (~0.35 s of device work), so that a fresh box has left its idle
+    # power state before the timed region (a 23.2 ms first step-set was seen once against the usual 22.6 ms).  The
+    # count is the same on every rank: each step carries a collective.
+    n_warm = max(W, 3) + 15
     for _ in range(n_warm):
         step()
-    torch.cuda.synchronize()
-    t_w = time.perf_counter()
-    while time.perf_counter() - t_w < 0.4:
-        step()
-        torch.cuda.synchronize()
-        n_warm += 1
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks.start()
