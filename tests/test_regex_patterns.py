@@ -79,3 +79,42 @@ def test_capture_resolution_accepts_rust_flag_groups():
                       (r"(?u)subject:(\w+) (\w+)", ["Hi", "there"]), (r"(?<n>ID): (\w+)", ["ID", "abc9"])):
         idx = list(range(1, len(want) + 1))
         assert z.compile_regex_parts([RegexPattern(pat, idx)], hay)[0].captures == want, pat
+
+
+def test_unicode_general_category_classes():
+    r"""\p{..} / \P{..} with general categories against Python's unicodedata (the tables are generated from it)."""
+    import unicodedata
+    import pytest
+    cat = unicodedata.category
+    text = "Hello Wörld ÀÉî ßtraße ΑΒγδ Жд 123 ٤٥٦ x_y — “quoted” €5 + ∑    end\t!"
+
+    def runs(pred):
+        out, i = [], 0
+        while i < len(text):
+            if pred(text[i]):
+                j = i
+                while j < len(text) and pred(text[j]):
+                    j += 1
+                out.append((len(text[:i].encode()), len(text[:j].encode())))
+                i = j
+            else:
+                i += 1
+        return out
+
+    cases = [(r"\p{Lu}+", lambda c: cat(c) == "Lu"), (r"\p{L}+", lambda c: cat(c)[0] == "L"), (r"\pL+", lambda c: cat(c)[0] == "L"),
+             (r"\p{Letter}+", lambda c: cat(c)[0] == "L"), (r"\p{Nd}+", lambda c: cat(c) == "Nd"), (r"\p{gc=Decimal_Number}+", lambda c: cat(c) == "Nd"),
+             (r"\P{L}+", lambda c: cat(c)[0] != "L"), (r"\p{^L}+", lambda c: cat(c)[0] != "L"), (r"\p{P}+", lambda c: cat(c)[0] == "P"),
+             (r"\p{Sc}+", lambda c: cat(c) == "Sc"), (r"\p{Sm}+", lambda c: cat(c) == "Sm"), (r"\p{Z}+", lambda c: cat(c)[0] == "Z"),
+             (r"[\p{Lu}\p{Nd}]+", lambda c: cat(c) in ("Lu", "Nd")), (r"[^\p{L}\p{Z}]+", lambda c: cat(c)[0] not in "LZ"),
+             (r"\p{Ll}+", lambda c: cat(c) == "Ll"), (r"\p{ASCII}+", lambda c: ord(c) < 128)]
+    hay = text.encode()
+    for pat, pred in cases:
+        d = z.compile_regex(pat)
+        cnt, spans = oracle.dfa_find_iter(d.fwd, d.bwd, hay)
+        want = runs(pred)
+        assert [tuple(s) for s in spans[:cnt]] == want, pat
+        row = np.asarray(emu.dfa_scan(d.fwd, d.bwd, [hay]))[0]
+        assert int(row[0]) == cnt and (int(row[1]), int(row[2])) == want[0], pat
+    for pat in (r"\p{Greek}", r"(?-u)\p{L}", r"(?i)\p{Lu}", r"\p{", r"\p{Xx}"):
+        with pytest.raises(z.RegexError):
+            z.compile_regex(pat)

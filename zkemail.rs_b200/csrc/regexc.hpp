@@ -17,8 +17,9 @@
 // named), alternation, greedy and lazy * + ? {m} {m,} {m,n}, anchors ^ $ \A \z, flags i m s U u.
 // ASCII word boundaries ((?-u:\b), (?-u:\B)) are resolved by the determiniser (one "previous byte was a word byte"
 // bit per state, as regex-automata does).
-// Rejected (ZKB_E_REGEX): Unicode word boundaries (no dense DFA exists for them), Unicode property classes (\p),
-// class set operations, back-references, the x flag.
+// \p{..} / \P{..} with Unicode general categories (Lu, L, Letter, gc=Nd, ...), Any and ASCII.
+// Rejected (ZKB_E_REGEX): Unicode word boundaries (no dense DFA exists for them), Unicode scripts and other
+// non-category properties, class set operations, back-references, the x flag.
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -89,6 +90,7 @@ struct Parser {
   std::string err;
   int depth = 0;
   bool cur_unicode = true;   // the u flag in effect where an escape is being parsed
+  bool cur_icase = false;    // the i flag in effect there
 
   Parser(const char* s, size_t len) : p((const uint8_t*)s), n(len) {}
   int add(const Node& nd) { nodes.push_back(nd); return (int)nodes.size() - 1; }
@@ -175,6 +177,69 @@ struct Parser {
     }
     return false;
   }
+  // \p{..} / \P{..} / \pL: Unicode general categories (two-letter values, their one-letter groups, long names,
+  // gc= / General_Category= prefixes, \p{^..} negation, Any, ASCII).  Scripts and other properties are rejected:
+  // the tables come from Python's unicodedata, which only exposes the general category.
+  bool unicode_property(bool negated, RangeSet& out, bool& neg) {
+    if (!cur_unicode) return fail("Unicode class not allowed under (?-u)");
+    if (cur_icase) return fail("Unicode class under (?i) is not supported (no case-folding tables for it)");
+    std::string name;
+    if (pos < n && p[pos] == '{') {
+      size_t a = ++pos;
+      while (pos < n && p[pos] != '}') pos++;
+      if (pos >= n) return fail("unclosed Unicode class");
+      name.assign((const char*)p + a, pos - a);
+      pos++;
+    } else if (pos < n) {
+      name.assign(1, (char)p[pos++]);
+    } else return fail("incomplete Unicode class");
+    bool inner_neg = false;
+    std::string k;
+    for (char c : name) {
+      if (c == ' ' || c == '_' || c == '-') continue;
+      k.push_back((char)((c >= 'A' && c <= 'Z') ? c + 32 : c));
+    }
+    if (!k.empty() && k[0] == '^') { inner_neg = true; k.erase(0, 1); }
+    for (const char* pre : {"generalcategory=", "generalcategory:", "gc=", "gc:"})
+      if (k.compare(0, strlen(pre), pre) == 0) { k.erase(0, strlen(pre)); break; }
+    static const struct { const char* longname; const char* cats; } NAMES[] = {
+        {"letter", "lu ll lt lm lo"}, {"l", "lu ll lt lm lo"}, {"casedletter", "lu ll lt"}, {"lc", "lu ll lt"},
+        {"uppercaseletter", "lu"}, {"lowercaseletter", "ll"}, {"titlecaseletter", "lt"}, {"modifierletter", "lm"}, {"otherletter", "lo"},
+        {"mark", "mn mc me"}, {"m", "mn mc me"}, {"combiningmark", "mn mc me"}, {"nonspacingmark", "mn"}, {"spacingmark", "mc"}, {"enclosingmark", "me"},
+        {"number", "nd nl no"}, {"n", "nd nl no"}, {"decimalnumber", "nd"}, {"digit", "nd"}, {"letternumber", "nl"}, {"othernumber", "no"},
+        {"punctuation", "pc pd ps pe pi pf po"}, {"p", "pc pd ps pe pi pf po"}, {"punct", "pc pd ps pe pi pf po"},
+        {"connectorpunctuation", "pc"}, {"dashpunctuation", "pd"}, {"openpunctuation", "ps"}, {"closepunctuation", "pe"},
+        {"initialpunctuation", "pi"}, {"finalpunctuation", "pf"}, {"otherpunctuation", "po"},
+        {"symbol", "sm sc sk so"}, {"s", "sm sc sk so"}, {"mathsymbol", "sm"}, {"currencysymbol", "sc"}, {"modifiersymbol", "sk"}, {"othersymbol", "so"},
+        {"separator", "zs zl zp"}, {"z", "zs zl zp"}, {"spaceseparator", "zs"}, {"lineseparator", "zl"}, {"paragraphseparator", "zp"},
+        {"other", "cc cf co cn"}, {"c", "cc cf co cn"}, {"control", "cc"}, {"cntrl", "cc"}, {"format", "cf"}, {"privateuse", "co"}, {"unassigned", "cn"},
+    };
+    std::string cats;
+    if (k == "any") { out = {Range(0, 0x10FFFF)}; neg = negated != inner_neg; return true; }
+    if (k == "ascii") { out = {Range(0, 0x7F)}; neg = negated != inner_neg; return true; }
+    for (auto& nm : NAMES) if (k == nm.longname) { cats = nm.cats; break; }
+    if (cats.empty() && k.size() == 2) cats = k;
+    out.clear();
+    size_t a = 0;
+    while (a < cats.size()) {
+      size_t b = cats.find(' ', a);
+      if (b == std::string::npos) b = cats.size();
+      const std::string c2 = cats.substr(a, b - a);
+      bool found = false;
+      for (size_t i = 0; i < UNI_GC_N; i++)
+        if (c2 == UNI_GC[i].name) {
+          for (size_t j = 0; j < UNI_GC[i].n; j++) out.push_back(Range(UNI_GC[i].r[j][0], UNI_GC[i].r[j][1]));
+          found = true;
+          break;
+        }
+      if (!found) { out.clear(); break; }
+      a = b + 1;
+    }
+    if (out.empty()) return fail("unsupported Unicode property (general categories only)");
+    normalize(out);
+    neg = negated != inner_neg;
+    return true;
+  }
   bool hex_digits(int count, uint32_t& v) {
     v = 0;
     for (int k = 0; k < count; k++) {
@@ -216,6 +281,7 @@ struct Parser {
       case 'a': c = 0x07; return 0;
       case 'x': case 'u': case 'U': return hex_escape(e, c) ? 0 : -1;
       case 'd': case 'D': case 'w': case 'W': case 's': case 'S': perl_class(e, cls, neg, cur_unicode); return 1;
+      case 'p': case 'P': return unicode_property(e == 'P', cls, neg) ? 1 : -1;
       case 'A': if (in_class) break; look = LOOK_START_TEXT; return 2;
       case 'z': if (in_class) break; look = LOOK_END_TEXT; return 2;
       case 'b': case 'B':
@@ -266,6 +332,7 @@ struct Parser {
   }
   int parse_class(const Flags& f) {  // at '['
     cur_unicode = f.u;
+    cur_icase = f.i;
     pos++;
     bool negated = false;
     if (pos < n && p[pos] == '^') { negated = true; pos++; }
@@ -429,6 +496,7 @@ struct Parser {
     if (c == '\\') {
       pos++;
       cur_unicode = f.u;
+      cur_icase = f.i;
       uint32_t lit; RangeSet cls; bool neg; int look;
       int k = escape(lit, cls, neg, look, false);
       if (k < 0) return -1;
