@@ -102,9 +102,9 @@ class ClockSampler:
 
 
 def build_pool(wl, n_emails, unique, seed, threads, log):
-    """Seeded synthetic pool (oracle/zk_gen.c).  Returns (MailPool, order) where order repeats the
+    """Seeded synthetic pool (workload/zk_gen.c).  Returns (MailPool, order) where order repeats the
     unique signed emails (in arena order) up to n_emails when unique < n_emails."""
-    from oracle import gen
+    import workload as gen
     t0 = time.time()
     keys = gen.KeyPool(wl["keys2048"], wl["keys1024"], threads)
     t_keys = time.time() - t0

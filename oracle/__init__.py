@@ -21,7 +21,7 @@ STATUS_NAMES = {
 
 
 def build(force: bool = False) -> str:
-    src = [os.path.join(_HERE, f) for f in ("zk_oracle.c", "zk_oracle.h", "zk_gen.c")]
+    src = [os.path.join(_HERE, f) for f in ("zk_oracle.c", "zk_oracle.h")]
     src = [s for s in src if os.path.exists(s)]
     if force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src

@@ -9,7 +9,7 @@ import pytest
 
 import oracle
 import zkemail_rs_b200 as z
-from oracle import gen
+import workload as gen
 from zkemail_rs_b200.engine import EmailViews, RESULT_DTYPE
 from zkemail_rs_b200.structs import CompiledRegex, RegexInfo
 from tests.util import NOW

@@ -1,5 +1,5 @@
 """The oracle's DKIM path against mail signed by the independent Python signer (synth.py, written
-from RFC 6376) and by the C/OpenSSL generator (oracle/zk_gen.c): a signature either verifies or it
+from RFC 6376) and by the C/OpenSSL generator (workload/zk_gen.c): a signature either verifies or it
 does not, so agreement of three independent implementations pins canonicalisation, header
 selection and the RSA step."""
 import hashlib
@@ -34,7 +34,7 @@ def test_positive_and_negative_classes():
 
 
 def test_c_generator_agrees_with_oracle():
-    from oracle import gen
+    import workload as gen
     kp = gen.KeyPool(3, 2, threads=4)
     mp = gen.MailPool(kp, 240, np.random.default_rng(3).integers(0, 6000, size=240), neg_fraction=0.1,
                       token=True, qp_percent=30, threads=4)

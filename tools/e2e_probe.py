@@ -5,7 +5,7 @@ os.environ["ZKB_PROFILE"] = "1"
 import numpy as np
 import zkemail_rs_b200 as z
 from zkemail_rs_b200.engine import EmailViews
-from oracle import gen
+import workload as gen
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
 kp = gen.KeyPool(256, 0)
 t = time.time(); mp = gen.MailPool(kp, N, 4096, neg_fraction=0.01); print("gen %.1fs" % (time.time() - t), flush=True)

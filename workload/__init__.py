@@ -1,4 +1,5 @@
-"""ctypes front end of oracle/zk_gen.c (TEST/BENCH INFRASTRUCTURE): large seeded pools of
+"""Synthetic workload generator — ctypes front end of workload/zk_gen.c (BENCH / TEST INFRASTRUCTURE, neither product
+code nor the oracle): large seeded pools of
 DKIM-signed synthetic mail as flat numpy arrays, plus zero-copy views for the engine's C ABI
 (zkb_email_view records) and for the oracle's batch driver (zo_email records)."""
 from __future__ import annotations

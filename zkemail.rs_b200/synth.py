@@ -4,7 +4,7 @@ needs DNS/HTTP for the key) and an INDEPENDENT RFC 6376 canonicaliser written fr
 this canonicaliser pin the C oracle and the CUDA path from a third, independent implementation.
 
 Pure Python + `cryptography`; used by tests/ and by bench.py for small pools.  (bench.py's large
-pools are produced by the C generator in oracle/zk_gen.c with the same recipe.)
+pools are produced by the C generator in workload/zk_gen.c with the same recipe.)
 """
 from __future__ import annotations
 
