@@ -304,7 +304,7 @@ def test_differential_fuzz_of_the_front_ends():
 
 
 def test_concurrent_callers(engine):
-    """INTEGRATION.md §6: calls on one engine are serialised, distinct engines are independent — four threads, two
+    """INTEGRATION.md §7: calls on one engine are serialised, distinct engines are independent — four threads, two
     engines, every result identical to the single-threaded one."""
     import threading
     emails, _ = mixed_emails(seed=41, n_pos=40)
