@@ -118,3 +118,24 @@ def test_unicode_general_category_classes():
     for pat in (r"\p{Greek}", r"(?-u)\p{L}", r"(?i)\p{Lu}", r"\p{", r"\p{Xx}"):
         with pytest.raises(z.RegexError):
             z.compile_regex(pat)
+
+
+def test_unicode_simple_case_folding():
+    """(?i) uses Unicode simple case folding (CaseFolding C + S), as the Rust regex crate does: the folding classes of
+    non-ASCII letters are honoured, the Turkic dotted / dotless i are NOT folded onto i (Python's re does fold them)."""
+    text = "É é STRASSE Straße ẞ Я я K k K s S ſ ǅ Ǆ ǆ σ ς Σ İ i I ı µ Μ μ Ꭰ ꭰ ÿ Ÿ"
+    hay = text.encode()
+
+    def found(pat):
+        d = z.compile_regex("(?i)" + pat)
+        cnt, spans = oracle.dfa_find_iter(d.fwd, d.bwd, hay)
+        row = np.asarray(emu.dfa_scan(d.fwd, d.bwd, [hay]))[0]
+        assert int(row[0]) == cnt
+        return [hay[s:e].decode() for s, e in spans[:cnt]]
+
+    for pat in ("é", "я", "k", "s", "ǆ", "σ", "ß", "ẞ", "µ", "ꭰ", "ÿ", "[а-я]", "[α-ω]"):
+        assert found(pat) == [m.group() for m in re.finditer(pat, text, re.IGNORECASE)], pat
+    assert found("i") == ["i", "I"] and found("ı") == ["ı"] and found("İ") == ["İ"]
+    # byte mode folds ASCII letters only
+    d = z.compile_regex(r"(?i-u)[a-z]+")
+    assert oracle.dfa_find_iter(d.fwd, d.bwd, b"abC \xc3\x89")[1][:2] == [(0, 3)]

@@ -14,7 +14,8 @@
 // Supported syntax: literals, escapes (\n \r \t \f \v \a \xHH \x{H..} \u{H..} \uHHHH and escaped
 // punctuation), `.`, classes with ranges / negation / POSIX names / nested \d \w \s, \d \w \s \D \W \S
 // (Unicode definitions in (?u) mode from generated tables, ASCII under (?-u)), groups (capturing, non-capturing,
-// named), alternation, greedy and lazy * + ? {m} {m,} {m,n}, anchors ^ $ \A \z, flags i m s U u.
+// named), alternation, greedy and lazy * + ? {m} {m,} {m,n}, anchors ^ $ \A \z, flags i m s U u ((?i) = Unicode
+// simple case folding, ASCII-only under (?-u)).
 // ASCII word boundaries ((?-u:\b), (?-u:\B)) are resolved by the determiniser (one "previous byte was a word byte"
 // bit per state, as regex-automata does).
 // \p{..} / \P{..} with Unicode general categories (Lu, L, Letter, gc=Nd, ...), Any and ASCII.
@@ -111,26 +112,58 @@ struct Parser {
     pos += w;
     return true;
   }
-  static void fold_case(RangeSet& r) {  // simple case folding: ASCII plus the two non-ASCII code
-    RangeSet add;                        // points that fold onto ASCII letters (U+017F, U+212A)
-    for (auto& x : r) {
-      uint32_t lo = std::max<uint32_t>(x.first, 'a'), hi = std::min<uint32_t>(x.second, 'z');
-      if (lo <= hi) add.push_back(Range(lo - 32, hi - 32));
-      lo = std::max<uint32_t>(x.first, 'A'); hi = std::min<uint32_t>(x.second, 'Z');
-      if (lo <= hi) add.push_back(Range(lo + 32, hi + 32));
-      auto has = [&](uint32_t c) { return x.first <= c && c <= x.second; };
-      if (has('s') || has('S')) add.push_back(Range(0x17F, 0x17F));
-      if (has('k') || has('K')) add.push_back(Range(0x212A, 0x212A));
-      if (has(0x17F)) { add.push_back(Range('s', 's')); add.push_back(Range('S', 'S')); }
-      if (has(0x212A)) { add.push_back(Range('k', 'k')); add.push_back(Range('K', 'K')); }
+  // Simple case folding (Unicode CaseFolding C + S, tables from tools/gen_unicode_tables.py): every code point of
+  // the set drags in the other members of its folding class (k K U+212A; s S U+017F; sigma, final sigma, Sigma; ...).
+  static const std::vector<std::vector<uint32_t>>& fold_classes() {
+    static const std::vector<std::vector<uint32_t>> classes = [] {
+      std::map<uint32_t, std::vector<uint32_t>> by_fold;
+      for (size_t i = 0; i < UNI_FOLD_N; i++) by_fold[UNI_FOLD[i][1]].push_back(UNI_FOLD[i][0]);
+      std::vector<std::vector<uint32_t>> out;
+      for (auto& kv : by_fold) {
+        std::vector<uint32_t> c = kv.second;
+        c.push_back(kv.first);
+        std::sort(c.begin(), c.end());
+        out.push_back(c);
+      }
+      return out;
+    }();
+    return classes;
+  }
+  static void fold_case(RangeSet& r, bool unicode) {
+    normalize(r);
+    if (!unicode) {   // (?i-u): bytes, ASCII letters only
+      RangeSet add;
+      for (auto& x : r) {
+        uint32_t lo = std::max<uint32_t>(x.first, 'a'), hi = std::min<uint32_t>(x.second, 'z');
+        if (lo <= hi) add.push_back(Range(lo - 32, hi - 32));
+        lo = std::max<uint32_t>(x.first, 'A'); hi = std::min<uint32_t>(x.second, 'Z');
+        if (lo <= hi) add.push_back(Range(lo + 32, hi + 32));
+      }
+      r.insert(r.end(), add.begin(), add.end());
+      normalize(r);
+      return;
+    }
+    auto has = [&](uint32_t c) {
+      size_t lo = 0, hi = r.size();
+      while (lo < hi) {
+        size_t mid = (lo + hi) / 2;
+        if (r[mid].second < c) lo = mid + 1; else hi = mid;
+      }
+      return lo < r.size() && r[lo].first <= c;
+    };
+    RangeSet add;
+    for (auto& cls : fold_classes()) {
+      bool any = false;
+      for (uint32_t c : cls) if (has(c)) { any = true; break; }
+      if (any) for (uint32_t c : cls) add.push_back(Range(c, c));
     }
     r.insert(r.end(), add.begin(), add.end());
     normalize(r);
   }
   int make_class(RangeSet r, const Flags& f, bool negated) {
     if (f.i) {
-      fold_case(r);
-      if (!f.u) {  // byte mode folds ASCII only
+      fold_case(r, f.u);
+      if (!f.u) {  // byte mode: nothing above 0xFF
         RangeSet t;
         for (auto& x : r) if (x.first <= 0xFF) t.push_back(Range(x.first, std::min<uint32_t>(x.second, 0xFF)));
         r.swap(t);
