@@ -2,8 +2,9 @@
 library's reader (csrc/ra_wire.hpp) without a Rust toolchain.  It lays a ZDF1 table out the way
 dense::DFA::to_bytes_little_endian does as restated in SURVEY.md §8a R5 (regex-automata 0.4.9, a Cargo.lock
 dependency absent from /root/reference): label, endianness check, version, flags, transition table with
-premultiplied ids, start table, match states, special states, accelerators, quit set.  Parity of this layout
-with real crate output is UNPINNED — the round trip only proves that reader and restated layout agree."""
+premultiplied ids, start table, match states, special states, accelerators, quit set.  The layout is PINNED by
+two blobs written by the crate itself (tests/golden/ra_dense_ws_{fwd,rev}.bin, see extract_bstr_dfas.py):
+re-serialising their parsed form through this writer reproduces them byte for byte (tests/test_ra_wire.py)."""
 from __future__ import annotations
 
 import struct
@@ -20,7 +21,10 @@ def parse_zdf(z: bytes) -> dict:
     return dict(flags=flags, ns=ns, nc=nc, mn=mn, mx=mx, start=start, classes=z[72:328], start_map=z[328:584], trans=trans)
 
 
-def zdf_to_wire(z: bytes, flag_words: int = 1, with_quit_state: bool = False) -> bytes:
+def zdf_to_wire(z: bytes, with_quit_state: bool = False, has_quit_state: bool = False, start_kind=None) -> bytes:
+    """with_quit_state inserts an unreachable quit state as state 1 (what the crate's determinizer always emits);
+    has_quit_state says state 1 of `z` already is that state.  start_kind: 0 both, 1 unanchored, 2 anchored
+    (default: anchored for reverse tables, both otherwise — what dfa::regex::Builder produces)."""
     d = parse_zdf(z)
     ns, nc = d["ns"], d["nc"]
     stride2 = max(1, (nc - 1).bit_length())
@@ -33,14 +37,18 @@ def zdf_to_wire(z: bytes, flag_words: int = 1, with_quit_state: bool = False) ->
     out = bytearray(LABEL + b"\0" * (-len(LABEL) % 4))
     out += struct.pack("<3I", 0xFEFF, 2, 0)
     has_empty, is_utf8 = (d["flags"] >> 2) & 1, (d["flags"] >> 1) & 1
-    out += struct.pack("<I", has_empty | (is_utf8 << 1)) if flag_words == 1 else struct.pack("<3I", has_empty, is_utf8, 0)
+    out += struct.pack("<I", has_empty | (is_utf8 << 1))
     out += struct.pack("<2I", ns, stride2) + d["classes"]
     table = [0] * (ns << stride2)
     for s in range(d["ns"]):
         for c in range(nc):
             table[sid(s) + c] = sid(d["trans"][s * nc + c])
     out += struct.pack(f"<{len(table)}I", *table)
-    out += struct.pack("<I", 2 if d["flags"] & 1 else 0) + d["start_map"] + struct.pack("<4I", 6, MAX, MAX, MAX)
+    if start_kind is None:
+        start_kind = 2 if d["flags"] & 1 else 0
+    # a universal start state exists when the look-behind byte does not matter (all six kinds share one state)
+    uni = [sid(h[0]) if len(set(h)) == 1 and h[0] != 0 else MAX for h in (d["start"][:6], d["start"][6:])]
+    out += struct.pack("<I", start_kind) + d["start_map"] + struct.pack("<4I", 6, MAX, uni[0], uni[1])
     out += struct.pack("<12I", *[sid(s) for s in d["start"]])
     has_match = d["mn"] <= d["mx"] < d["ns"]
     n_match = d["mx"] - d["mn"] + 1 if has_match else 0
@@ -49,7 +57,7 @@ def zdf_to_wire(z: bytes, flag_words: int = 1, with_quit_state: bool = False) ->
         out += struct.pack("<2I", i, 1)
     out += struct.pack("<2I", 1, n_match) + struct.pack(f"<{n_match}I", *([0] * n_match))
     mn, mx = (sid(d["mn"]), sid(d["mx"])) if has_match else (0, 0)
-    quit_id = stride if with_quit_state else 0
+    quit_id = stride if (with_quit_state or has_quit_state) else 0
     out += struct.pack("<8I", max(mx, quit_id), quit_id, mn, mx, 0, 0, 0, 0)
     out += struct.pack("<I", 0) + b"\0" * 32
     return bytes(out)

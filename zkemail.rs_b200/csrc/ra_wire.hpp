@@ -3,16 +3,16 @@
 // The reference ships `DFA.fwd` / `DFA.bwd` as `dense::DFA::to_bytes_little_endian()` output with the leading
 // alignment padding removed (helpers/src/regex.rs:7-14) and loads them with `dense::DFA::from_bytes`
 // (core/src/regex.rs:32-33).  regex-automata 0.4.9 is a Cargo.lock dependency absent from /root/reference and no
-// Rust toolchain exists here, so the layout below is restated from the crate's documented format and
-// is UNPINNED against real crate output: the reader therefore validates every section, requires the sections to
-// consume the blob exactly, and rejects anything else (ZKB_E_REGEX) instead of guessing.  It converts to the
-// engine's own ZDF1 table (include/zkemail_b200.h), which models the same automaton: premultiplied ids become
+// Rust toolchain exists here; the layout below is restated from the crate's format and PINNED by two
+// blobs the crate itself wrote (tests/golden/ra_dense_ws_{fwd,rev}.bin: the `\s+` dense DFAs the bstr crate embeds,
+// format version 2; tests/test_ra_wire.py), which settled the flags word as ONE u32 bitset.  The reader validates
+// every section, requires the sections to consume the blob exactly, and rejects anything else (ZKB_E_REGEX)
+// instead of guessing.  It converts to the engine's own ZDF1 table (include/zkemail_b200.h), which models the same automaton: premultiplied ids become
 // state indices, match states stay one contiguous range entered one byte late, the last alphabet class is EOI.
 //
 //   label   "rust-regex-automata-dfa-dense" NUL, zero-padded to a multiple of 4      (32 bytes)
 //   u32     0xFEFF endianness check, u32 version (2), u32 unused
-//   flags   u32 bitset (bit0 has_empty, bit1 is_utf8, bit2 always_start_anchored); a 3-word form (one u32 per
-//           flag) is also accepted when it is the only reading under which the rest of the blob validates
+//   flags   u32 bitset (bit0 has_empty, bit1 is_utf8, bit2 always_start_anchored)
 //   transitions  u32 state_len, u32 stride2, u8 classes[256], u32 next[state_len << stride2]
 //   starts  u32 kind, u8 start_map[256], u32 stride (6), u32 pattern_len | MAX, u32 universal unanchored | MAX,
 //           u32 universal anchored | MAX, u32 ids[2 * stride (+ stride * pattern_len)]
@@ -46,21 +46,14 @@ struct Cursor {
 
 inline void wr32(std::vector<uint8_t>& o, size_t at, uint32_t v) { for (int i = 0; i < 4; i++) o[at + i] = (uint8_t)(v >> (8 * i)); }
 
-// one attempt with `flag_words` words of flags; on success fills zdf
-inline bool to_zdf_with(const uint8_t* b, size_t n, bool reverse, int flag_words, std::vector<uint8_t>& zdf) {
+inline bool to_zdf(const uint8_t* b, size_t n, bool reverse, std::vector<uint8_t>& zdf) {
+  if (!is_wire(b, n)) return false;
   Cursor c{b, n, 32};
   uint32_t endian, version, unused;
   if (!c.u32(endian) || !c.u32(version) || !c.u32(unused) || endian != 0xFEFFu || version != 2u) return false;
-  bool has_empty, is_utf8;
-  if (flag_words == 1) {
-    uint32_t bits;
-    if (!c.u32(bits) || bits > 7u) return false;
-    has_empty = bits & 1u; is_utf8 = bits & 2u;
-  } else {
-    uint32_t f0, f1, f2;
-    if (!c.u32(f0) || !c.u32(f1) || !c.u32(f2) || f0 > 1u || f1 > 1u || f2 > 1u) return false;
-    has_empty = f0; is_utf8 = f1;
-  }
+  uint32_t bits;
+  if (!c.u32(bits) || bits > 7u) return false;
+  const bool has_empty = bits & 1u, is_utf8 = bits & 2u;
   // transition table
   uint32_t state_len, stride2;
   if (!c.u32(state_len) || !c.u32(stride2) || state_len == 0 || stride2 < 1 || stride2 > 9 || state_len > (1u << 24)) return false;
@@ -142,16 +135,6 @@ inline bool to_zdf_with(const uint8_t* b, size_t n, bool reverse, int flag_words
   for (uint32_t s = 0; s < state_len; s++)
     for (uint32_t k = 0; k < alphabet; k++)
       wr32(zdf, ZKB_ZDF_HEADER + 4 * ((size_t)s * alphabet + k), rd32(table + 4 * (((uint64_t)s << stride2) + k)) >> stride2);
-  return true;
-}
-
-inline bool to_zdf(const uint8_t* b, size_t n, bool reverse, std::vector<uint8_t>& zdf) {
-  if (!is_wire(b, n)) return false;
-  std::vector<uint8_t> a1, a3;
-  const bool ok1 = to_zdf_with(b, n, reverse, 1, a1);
-  const bool ok3 = to_zdf_with(b, n, reverse, 3, a3);
-  if (ok1 == ok3) return false;   // neither reading validates, or the blob is ambiguous: refuse
-  zdf.swap(ok1 ? a1 : a3);
   return true;
 }
 
