@@ -102,12 +102,23 @@ typedef struct {
   const zkb_capture *caps; size_t n_caps;
 } zkb_email_captures;
 
+/* zkb_options.flags: path switches for diagnosis and A/B runs (every path gives identical results).  The library reads
+ * no environment variables. */
+enum {
+  ZKB_OPT_NO_DIRECT = 1u,          /* ignore registered caller memory: raw messages are staged like pageable ones   */
+  ZKB_OPT_NO_DEVICE_FRONTEND = 2u, /* header parsing / canonicalisation / base64 on the host threads for every mail */
+  ZKB_OPT_NO_STAGED_FRONTEND = 4u, /* pageable callers: host front end instead of staging raw bytes for the device  */
+  ZKB_OPT_NO_OVERLAP = 8u,         /* resident batches: one stream instead of the two-stream schedule               */
+  ZKB_OPT_PROFILE = 16u,           /* per-call host / stream time breakdown on stderr                               */
+  ZKB_OPT_ALL = 31u
+};
+
 typedef struct {
   int32_t device;        /* CUDA device ordinal */
   int32_t host_threads;  /* 0 = all hardware threads */
   int64_t now_unix;      /* clock for the x= tag check; 0 = wall clock (cfdkim behaviour) */
   uint64_t chunk_emails; /* emails per pipeline chunk; 0 = default */
-  uint32_t flags;        /* reserved, 0 */
+  uint32_t flags;        /* ZKB_OPT_* bits, 0 = defaults */
   uint32_t rsa_lanes;    /* lanes cooperating on one signature (0 = default) */
 } zkb_options;
 
@@ -121,6 +132,8 @@ const char *zkb_strerror(int code);
 /* Engine = device context, streams, pinned staging, device arenas, key table. One per device. */
 int zkb_engine_create(const zkb_options *opt, zkb_engine **out);
 void zkb_engine_destroy(zkb_engine *e);
+/* Replaces the engine's ZKB_OPT_* bits; takes effect with the next call on the engine. */
+int zkb_engine_set_flags(zkb_engine *e, uint32_t flags);
 
 /* Optional zero-copy input path.  Registers caller memory holding raw messages with the CUDA driver
  * (page-locks it; cudaHostRegister).  Batches whose zkb_email_view.raw_email pointers all lie inside

@@ -260,19 +260,20 @@ def test_status_codes_registered_memory(engine):
     assert [int(g["status"]) for g in got][:5] == [0, 1, 1, 2, 9]
 
 
-def test_front_end_paths_agree(engine, monkeypatch):
+def test_front_end_paths_agree(engine):
     """One mixed batch through the three input paths — staged device front end (pageable views, the default),
-    host front end (ZKB_NO_DEVICE_FRONTEND) and registered memory — gives identical records, equal to the oracle's."""
+    host front end (ZKB_OPT_NO_DEVICE_FRONTEND) and registered memory — gives identical records, equal to the oracle's."""
     from tests.util import contiguous_views
     emails, _ = mixed_emails(seed=17, n_pos=48)
     exp = oracle.verify_batch(emails, now=NOW)
     staged = engine.verify_batch(emails)
-    import os
-    if not (os.environ.get("ZKB_NO_DEVICE_FRONTEND") or os.environ.get("ZKB_NO_STAGED_FRONTEND")):
-        assert engine.last_batch_bytes()["h2d_bytes"] > sum(len(e.raw_email) for e in emails)   # raw messages travelled
-    monkeypatch.setenv("ZKB_NO_DEVICE_FRONTEND", "1")
-    host = engine.verify_batch(emails)
-    monkeypatch.delenv("ZKB_NO_DEVICE_FRONTEND")
+    assert engine.last_batch_bytes()["h2d_bytes"] > sum(len(e.raw_email) for e in emails)   # raw messages travelled
+    engine.set_flags(z.OPT_NO_DEVICE_FRONTEND)
+    try:
+        host = engine.verify_batch(emails)
+        assert engine.last_batch_bytes()["host_front_end_emails"] == 0     # nothing was declined: nothing was tried
+    finally:
+        engine.set_flags(0)
     buf, views = contiguous_views(emails)
     engine.register_host(buf)
     try:

@@ -156,14 +156,12 @@ def test_resident_batch_matches_pipeline(engine):
     assert st["n_emails"] == len(emails) and st["kernel_launches"] >= 3
 
 
-@pytest.mark.parametrize("knobs", [{}, {"ZKB_NO_OVERLAP": "1"}])
-def test_resident_multi_chunk_overlapped_schedule(monkeypatch, knobs):
+@pytest.mark.parametrize("flags", [0, z.OPT_NO_OVERLAP])
+def test_resident_multi_chunk_overlapped_schedule(flags):
     """zkb_batch_run_async with several resident chunks: hashing of chunk k+1 on the side stream next to the RSA of
     chunk k (and the single-stream order) gives the records of the plain pipeline and of the oracle."""
     from zkemail_rs_b200.engine import EmailViews
-    for k, v in knobs.items():
-        monkeypatch.setenv(k, v)
-    eng = z.Engine(device=0, now_unix=NOW, chunk_emails=8)     # resident chunks hold 32 emails
+    eng = z.Engine(device=0, now_unix=NOW, chunk_emails=8, flags=flags)     # resident chunks hold 32 emails
     try:
         emails, _ = mixed_emails(seed=31, n_pos=150, with_token=True)
         info = RegexInfo(None, [CompiledRegex(z.compile_regex(r"Transaction ID: [A-Z0-9]+"), None)])
@@ -186,7 +184,6 @@ def test_direct_mode_device_canonicalisation(engine):
     """Zero-copy path: raw messages in registered host memory; headers parsed / preimages built / base64
     decoded by frontend.cuh and bodies canonicalised by canon.cuh on the device (irregular messages fall
     back to the host front end).  Must equal the oracle AND the two host-side paths record for record."""
-    import os
     from tests.util import contiguous_views
     emails, labels = mixed_emails(seed=31, with_token=True)
     rng = np.random.default_rng(32)
@@ -208,15 +205,12 @@ def test_direct_mode_device_canonicalisation(engine):
         got_res = pb.fetch()
         st = pb.stats()
         pb.close()
-        os.environ["ZKB_NO_DEVICE_FRONTEND"] = "1"      # registered memory, host front end + device canonicalisation
+        engine.set_flags(z.OPT_NO_DEVICE_FRONTEND)      # registered memory, host front end + device canonicalisation
         mid = engine.verify_views(views)
-        del os.environ["ZKB_NO_DEVICE_FRONTEND"]
-        os.environ["ZKB_NO_DIRECT"] = "1"               # everything on the host threads
+        engine.set_flags(z.OPT_NO_DIRECT | z.OPT_NO_DEVICE_FRONTEND)   # everything on the host threads
         host = engine.verify_views(views)
-        del os.environ["ZKB_NO_DIRECT"]
     finally:
-        os.environ.pop("ZKB_NO_DIRECT", None)
-        os.environ.pop("ZKB_NO_DEVICE_FRONTEND", None)
+        engine.set_flags(0)
         engine.unregister_host(buf)
     assert got.tobytes() == mid.tobytes()
     for g, e, lab in zip(got, exp, labels):

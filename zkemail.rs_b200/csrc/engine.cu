@@ -46,6 +46,31 @@ namespace {
     }                                                                                        \
   } while (0)
 
+// inside a loop that owns in-flight work: record the error and leave the loop; the common exit path cleans up
+#define CKB(expr)                                                                            \
+  {                                                                                          \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      fprintf(stderr, "[zkemail_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e),   \
+              __FILE__, __LINE__, cudaGetErrorString(_e));                                   \
+      rc = ZKB_E_CUDA;                                                                       \
+      break;                                                                                 \
+    }                                                                                        \
+  }
+
+// device temporaries of the kernel-level entry points: freed on every exit path
+struct DevTmp {
+  std::vector<void*> ptrs;
+  ~DevTmp() { for (void* p : ptrs) cudaFree(p); }
+  template <typename T> cudaError_t alloc(T** out, size_t bytes) {
+    void* p = nullptr;
+    cudaError_t r = cudaMalloc(&p, bytes ? bytes : 16);
+    if (r == cudaSuccess) ptrs.push_back(p);
+    *out = (T*)p;
+    return r;
+  }
+};
+
 // ------------------------------------------------------------------ thread pool
 // Parallel phases follow one another within microseconds in the chunk pipeline, so workers spin on a
 // generation counter for a short while before falling back to a condition variable.
@@ -315,6 +340,8 @@ struct zkb_engine {
   int64_t now_unix = 0;
   size_t chunk_emails = 65536;   // e2e pipeline chunk (also capped at 256 MB of raw bytes); resident batches use 4x
   uint32_t rsa_lanes = 4;   // lanes per 2048-bit signature (measured best on B200: 0.89 of the IMAD.WIDE peak)
+  std::atomic<uint32_t> flags{0};   // ZKB_OPT_* (zkb_options.flags / zkb_engine_set_flags)
+  bool has(uint32_t bit) const { return (flags.load(std::memory_order_relaxed) & bit) != 0; }
   ThreadPool* pool = nullptr;
   BlockPool blocks;
   Slot slots[3];
@@ -327,6 +354,7 @@ struct zkb_engine {
   std::vector<KeyMeta> key_meta;
   uint32_t* d_keytab = nullptr;
   size_t d_keytab_cap = 0, d_keytab_n = 0;
+  std::atomic<int> live_batches{0};   // resident batches hold key ids: the table is not trimmed while any is alive
   cudaEvent_t ev[8] = {nullptr};
   cudaStream_t aux_stream = nullptr;          // zkb_batch_run_async: hashing of the next chunk beside the RSA of this one
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -464,26 +492,34 @@ int32_t lookup_key(ThreadCtx& c, const uint8_t* der, size_t len, KeyMeta& meta) 
     return it->second.first;
   }
   zkb_engine* e = c.eng;
-  int32_t id;
+  int32_t id = -1;
   meta = KeyMeta();
+  bool known = false;
   {
     std::lock_guard<std::mutex> l(e->key_mu);
     auto g = e->key_index.find(k);
-    if (g != e->key_index.end()) id = g->second;
-    else {
-      RsaKeyInfo info;
-      if (!parse_rsa_public_key(der, len, info)) id = -1;
+    if (g != e->key_index.end()) { id = g->second; meta = e->key_meta[id]; known = true; }
+  }
+  if (!known) {
+    // DER decode and the Montgomery constants (~1 M limb operations for a 4096-bit modulus) run outside the lock;
+    // rejected keys are remembered by the calling thread only (c.key_cache), never in the engine-wide table
+    RsaKeyInfo info;
+    if (parse_rsa_public_key(der, len, info)) {
+      std::vector<uint32_t> ent(ZKB_KEY_STRIDE);
+      build_key_entry(info, ent.data());
+      std::lock_guard<std::mutex> l(e->key_mu);
+      auto g = e->key_index.find(k);
+      if (g != e->key_index.end()) id = g->second;   // another thread was faster
       else {
         id = (int32_t)e->key_meta.size();
-        e->keytab_host.resize((size_t)(id + 1) * ZKB_KEY_STRIDE);
-        build_key_entry(info, e->keytab_host.data() + (size_t)id * ZKB_KEY_STRIDE);
+        e->keytab_host.insert(e->keytab_host.end(), ent.begin(), ent.end());
         KeyMeta m;
         m.limbs_class = info.limbs_class; m.k = info.k; m.generic = info.e != 65537;
         e->key_meta.push_back(m);
+        e->key_index.emplace(k, id);
       }
-      e->key_index.emplace(k, id);
+      meta = e->key_meta[id];
     }
-    if (id >= 0) meta = e->key_meta[id];
   }
   c.key_cache.emplace(std::move(k), std::make_pair(id, meta));
   pk.p = der; pk.len = len; pk.id = id; pk.meta = meta;
@@ -726,7 +762,7 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
   // direct mode: every message of the chunk lies in one registered host range and the chunk's span is
   // not much larger than its payload -> one DMA of the raw span, bodies canonicalised on the device
   ch.direct = false; ch.span_host = nullptr; ch.span_bytes = 0; ch.n_canon = 0;
-  if (ne && !e->registered.empty() && !getenv("ZKB_NO_DIRECT")) {
+  if (ne && !e->registered.empty() && !e->has(ZKB_OPT_NO_DIRECT)) {
     const uint8_t* lo = emails[e0].raw_email;
     const uint8_t* hi = lo;
     size_t payload = 0;
@@ -745,9 +781,9 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
       }
     }
   }
-  ch.fe = allow_fe && !getenv("ZKB_NO_DEVICE_FRONTEND");
+  ch.fe = allow_fe && !e->has(ZKB_OPT_NO_DEVICE_FRONTEND);
   if (ch.fe && !ch.direct) {  // staged: arena offsets of the staged domains are 32-bit, so keep giant messages on the host path
-    if (getenv("ZKB_NO_STAGED_FRONTEND")) ch.fe = false;
+    if (e->has(ZKB_OPT_NO_STAGED_FRONTEND)) ch.fe = false;
     for (size_t i = 0; i < ne && ch.fe; i++) if (emails[e0 + i].raw_email_len > ((size_t)64 << 20)) ch.fe = false;
   }
   ch.staged = ch.fe && !ch.direct;
@@ -981,6 +1017,18 @@ int upload_chunk(zkb_engine* e, Chunk& ch, const zkb_regex_set* rs, DeviceChunk&
   d.dfa_out = (uint4*)(d.out.p + o_dfa);
   d.M = ch.M; d.C = ch.C; d.NE = (uint32_t)ch.ne; d.P = (uint32_t)P;
   return ZKB_OK;
+}
+
+// The key table is append-only WITHIN a call (key ids live in the call's device records) and bounded ACROSS calls:
+// once it holds more than kKeySoftCap keys and no resident batch refers to it, the next call starts from an empty
+// table.  A service fed ever-new keys therefore holds at most max(kKeySoftCap, distinct keys of one call) entries
+// (1056 bytes each on the host and in HBM) instead of growing for the engine's lifetime.
+constexpr size_t kKeySoftCap = 16384;
+void trim_keytab(zkb_engine* e) {
+  std::lock_guard<std::mutex> l(e->key_mu);
+  if (e->key_meta.size() <= kKeySoftCap || e->live_batches.load() != 0) return;
+  e->key_index.clear(); e->keytab_host.clear(); e->key_meta.clear();
+  e->d_keytab_n = 0;   // device rows are rewritten as the new ids are assigned (calls are serialised by run_mu)
 }
 
 int sync_keytab(zkb_engine* e, cudaStream_t stream) {
@@ -1316,31 +1364,34 @@ int zkb_engine_create(const zkb_options* opt, zkb_engine** out) {
     return ZKB_E_NO_DEVICE;
   }
   zkb_engine* e = new zkb_engine();
+#define CKE(expr) do { if ((expr) != cudaSuccess) { fprintf(stderr, "[zkemail_b200] CUDA error at %s:%d: %s\n", __FILE__, __LINE__, cudaGetErrorString(cudaGetLastError())); zkb_engine_destroy(e); return ZKB_E_CUDA; } } while (0)
   e->device = dev;
   e->sm_count = prop.multiProcessorCount;
   e->smem_optin = prop.sharedMemPerBlockOptin;
   e->now_unix = opt ? opt->now_unix : 0;
   if (opt && opt->chunk_emails) e->chunk_emails = (size_t)opt->chunk_emails;
   if (opt && opt->rsa_lanes) e->rsa_lanes = opt->rsa_lanes;
+  if (opt) e->flags.store(opt->flags);
   int nt = opt ? opt->host_threads : 0;
   if (nt <= 0) nt = (int)std::thread::hardware_concurrency();
   if (nt <= 0) nt = 1;
   if (nt > 256) nt = 256;
   e->pool = new ThreadPool(nt);
   for (auto& s : e->slots) {
-    CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-    CK(cudaEventCreate(&s.k0)); CK(cudaEventCreate(&s.k1)); CK(cudaEventCreate(&s.h0));
+    CKE(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CKE(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    CKE(cudaEventCreate(&s.k0)); CKE(cudaEventCreate(&s.k1)); CKE(cudaEventCreate(&s.h0));
   }
-  for (auto& ev : e->ev) CK(cudaEventCreate(&ev));
+  for (auto& ev : e->ev) CKE(cudaEventCreate(&ev));
   {
     int lo = 0, hi = 0;
-    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CK(cudaStreamCreateWithPriority(&e->aux_stream, cudaStreamNonBlocking, hi));
-    CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    CKE(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CKE(cudaStreamCreateWithPriority(&e->aux_stream, cudaStreamNonBlocking, hi));
+    CKE(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CKE(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   }
-  if (ensure_dfa_attr(e)) return ZKB_E_CUDA;
+  if (ensure_dfa_attr(e)) { zkb_engine_destroy(e); return ZKB_E_CUDA; }
+#undef CKE
   *out = e;
   return ZKB_OK;
 }
@@ -1400,6 +1451,12 @@ int zkb_engine_last_batch_bytes(const zkb_engine* e, uint64_t* h2d, uint64_t* d2
   return ZKB_OK;
 }
 
+int zkb_engine_set_flags(zkb_engine* e, uint32_t flags) {
+  if (!e || (flags & ~(uint32_t)ZKB_OPT_ALL)) return ZKB_E_INVALID;
+  e->flags.store(flags);
+  return ZKB_OK;
+}
+
 void* zkb_engine_stream(zkb_engine* e) { return e ? (void*)e->slots[0].stream : nullptr; }
 
 int zkb_regex_set_create(zkb_engine* e, const zkb_dfa_view* parts, size_t n_header, size_t n_body, int header_present,
@@ -1426,12 +1483,16 @@ int zkb_regex_set_create(zkb_engine* e, const zkb_dfa_view* parts, size_t n_head
     part.direct = direct;
     part.fwd_bytes = (uint32_t)fb.size(); part.rev_bytes = (uint32_t)rb.size();
     if (cudaMalloc((void**)&part.d_fwd, fb.size()) != cudaSuccess || cudaMalloc((void**)&part.d_rev, rb.size()) != cudaSuccess) {
+      if (part.d_fwd) cudaFree(part.d_fwd);
       zkb_regex_set_destroy(rs);
       return ZKB_E_NOMEM;
     }
     rs->parts.push_back(part);
-    CK(cudaMemcpy(part.d_fwd, fb.data(), fb.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(part.d_rev, rb.data(), rb.size(), cudaMemcpyHostToDevice));
+    if (cudaMemcpy(part.d_fwd, fb.data(), fb.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(part.d_rev, rb.data(), rb.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      zkb_regex_set_destroy(rs);
+      return ZKB_E_CUDA;
+    }
   }
   *out = rs;
   return ZKB_OK;
@@ -1482,7 +1543,7 @@ static int verify_batch_impl(zkb_engine* e, const zkb_email_view* emails, size_t
   Chunk chunks[3];
   bool busy[3] = {false, false, false};
   const size_t P = regex ? regex->n_active() : 0;
-  const bool prof = getenv("ZKB_PROFILE") != nullptr;
+  const bool prof = e->has(ZKB_OPT_PROFILE);
   double t_pack = 0, t_upload = 0, t_wait = 0, t_resolve = 0, t_all = now_s();
   double t_gpu_h2d = 0, t_gpu_kern = 0;   // device-side stream time (ms) of the copies / kernels, summed over chunks
   e->prof_parse = e->prof_layout = e->prof_prelude = 0; e->prof_busy_ns = 0;
@@ -1519,17 +1580,17 @@ static int verify_batch_impl(zkb_engine* e, const zkb_email_view* emails, size_t
     t_pack += t1 - t0;
     rc = sync_keytab(e, s.stream);
     if (rc) break;
-    if (prof) CK(cudaEventRecord(s.h0, s.stream));
+    if (prof) CKB(cudaEventRecord(s.h0, s.stream));
     rc = upload_chunk(e, ch, regex, s.dev, s.meta, s.stream);
     if (rc) break;
-    if (prof) CK(cudaEventRecord(s.k0, s.stream));
+    if (prof) CKB(cudaEventRecord(s.k0, s.stream));
     rc = launch_chunk(e, s.dev, regex, s.stream, nullptr, nullptr);
     if (rc) break;
-    if (prof) CK(cudaEventRecord(s.k1, s.stream));
+    if (prof) CKB(cudaEventRecord(s.k1, s.stream));
     e->last_h2d += ch.st.h2d_bytes; e->last_d2h += s.dev.out_bytes;
     if (!s.result.ensure(s.dev.out_bytes)) { rc = ZKB_E_NOMEM; break; }
-    CK(cudaMemcpyAsync(s.result.p, s.dev.out.p, s.dev.out_bytes, cudaMemcpyDeviceToHost, s.stream));
-    CK(cudaEventRecord(s.done, s.stream));
+    CKB(cudaMemcpyAsync(s.result.p, s.dev.out.p, s.dev.out_bytes, cudaMemcpyDeviceToHost, s.stream));
+    CKB(cudaEventRecord(s.done, s.stream));
     busy[si] = true;
     t_upload += now_s() - t1;
     // resolve the chunk launched two iterations ago: two chunks stay in flight (one in H2D, one in kernels)
@@ -1545,6 +1606,9 @@ static int verify_batch_impl(zkb_engine* e, const zkb_email_view* emails, size_t
   }
   for (int si = 0; si < 3; si++) {
     if (busy[si]) { int r2 = finish(si); if (rc == ZKB_OK) rc = r2; }
+    // error exit: copies out of this slot's pinned blocks may still be queued; they must finish before the blocks
+    // return to the pool and the stack-owned chunk records die
+    if (rc != ZKB_OK && e->slots[si].stream) cudaStreamSynchronize(e->slots[si].stream);
     release_blocks(e, chunks[si]);
   }
   (void)P;
@@ -1563,6 +1627,7 @@ int zkb_verify_batch(zkb_engine* e, const zkb_email_view* emails, size_t n, cons
   std::lock_guard<std::mutex> lock(e->run_mu);
   CK(cudaSetDevice(e->device));
   std::vector<size_t> fb;
+  trim_keytab(e);
   e->last_h2d = e->last_d2h = e->last_fallback = 0;
   int rc = verify_batch_impl(e, emails, n, regex, captures, out, true, &fb);
   e->last_fallback = fb.size();
@@ -1577,7 +1642,7 @@ int zkb_verify_batch(zkb_engine* e, const zkb_email_view* emails, size_t n, cons
   if (rc) return rc;
   const size_t rec_bytes = regex ? sizeof(zkb_result) : offsetof(zkb_result, parts);
   for (size_t i = 0; i < fb.size(); i++) memcpy(&out[fb[i]], &r2[i], rec_bytes);
-  if (getenv("ZKB_PROFILE")) fprintf(stderr, "[zkb profile] device front end declined %zu of %zu messages (host front end used)\n", fb.size(), n);
+  if (e->has(ZKB_OPT_PROFILE)) fprintf(stderr, "[zkb profile] device front end declined %zu of %zu messages (host front end used)\n", fb.size(), n);
   return ZKB_OK;
 }
 
@@ -1592,6 +1657,7 @@ void zkb_batch_destroy(zkb_batch* b) {
   if (b->eng) cudaSetDevice(b->eng->device);
   for (auto* c : b->chunks) { if (c) { release_blocks(b->eng, *c); delete c; } }
   for (auto* d : b->dev) { if (d) { d->free(); delete d; } }
+  if (b->eng) b->eng->live_batches.fetch_sub(1);
   delete b;
 }
 
@@ -1602,14 +1668,16 @@ int zkb_batch_prepare(zkb_engine* e, const zkb_email_view* emails, size_t n, con
   *out = nullptr;
   std::lock_guard<std::mutex> lock(e->run_mu);
   CK(cudaSetDevice(e->device));
+  trim_keytab(e);
   zkb_batch* b = new zkb_batch();
+  e->live_batches.fetch_add(1);
   b->eng = e; b->regex = regex; b->n = n; b->emails = emails; b->captures = captures;
   // resident batches: fewer, larger launches (better SM balance).  When the whole batch lies in registered memory
   // (raw bytes are DMA'd, nothing is staged in pinned blocks) a chunk may hold up to 16 GB, so that batches of large
   // messages still give the lane-per-message kernels tens of thousands of lanes per launch (100 KB bodies: 29 K
   // lanes per 3 GB chunk left the SHA-256 kernel latency-bound at 1.5 warps per scheduler).
   size_t max_bytes = (size_t)3 << 30;
-  if (n && !e->registered.empty() && !getenv("ZKB_NO_DIRECT")) {
+  if (n && !e->registered.empty() && !e->has(ZKB_OPT_NO_DIRECT)) {
     const uint8_t *lo = emails[0].raw_email, *hi = lo;
     for (size_t i = 0; i < n; i++) { lo = std::min(lo, emails[i].raw_email); hi = std::max(hi, emails[i].raw_email + emails[i].raw_email_len); }
     for (auto& r : e->registered)
@@ -1650,7 +1718,7 @@ int zkb_batch_run_async(zkb_batch* b) {
   CK(cudaSetDevice(e->device));
   cudaStream_t s = e->slots[0].stream;
   const size_t nc = b->dev.size();
-  if (nc < 2 || getenv("ZKB_NO_OVERLAP")) {
+  if (nc < 2 || e->has(ZKB_OPT_NO_OVERLAP)) {
     for (auto* d : b->dev) {
       // flags and DFA outputs accumulate with atomicOr / plain stores: reset them for a re-run
       size_t o_flags, o_dfa;
@@ -1852,8 +1920,9 @@ int zkb_sha256_batch(zkb_engine* e, const uint8_t* data, size_t data_len, const 
   std::vector<uint8_t> host(total + 64, 0);
   for (size_t i = 0; i < n; i++) if (len[i]) memcpy(host.data() + noff[i], data + off[i], len[i]);
   uint8_t* d_arena; uint64_t* d_off; uint32_t* d_len; uint32_t* d_dig;
-  CK(cudaMalloc((void**)&d_arena, host.size()));
-  CK(cudaMalloc((void**)&d_off, n * 8)); CK(cudaMalloc((void**)&d_len, n * 4)); CK(cudaMalloc((void**)&d_dig, n * 32));
+  DevTmp tmp;
+  CK(tmp.alloc(&d_arena, host.size()));
+  CK(tmp.alloc(&d_off, n * 8)); CK(tmp.alloc(&d_len, n * 4)); CK(tmp.alloc(&d_dig, n * 32));
   CK(cudaMemcpy(d_arena, host.data(), host.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_off, noff.data(), n * 8, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_len, len, n * 4, cudaMemcpyHostToDevice));
@@ -1864,7 +1933,6 @@ int zkb_sha256_batch(zkb_engine* e, const uint8_t* data, size_t data_len, const 
   std::vector<uint32_t> dig(n * 8);
   CK(cudaMemcpy(dig.data(), d_dig, n * 32, cudaMemcpyDeviceToHost));
   for (size_t i = 0; i < n * 8; i++) { out[4 * i] = (uint8_t)(dig[i] >> 24); out[4 * i + 1] = (uint8_t)(dig[i] >> 16); out[4 * i + 2] = (uint8_t)(dig[i] >> 8); out[4 * i + 3] = (uint8_t)dig[i]; }
-  cudaFree(d_arena); cudaFree(d_off); cudaFree(d_len); cudaFree(d_dig);
   return ZKB_OK;
 }
 
@@ -1874,6 +1942,7 @@ int zkb_rsa_verify_batch(zkb_engine* e, const uint8_t* const* key_der, const siz
   if (n == 0) return ZKB_OK;
   std::lock_guard<std::mutex> lock(e->run_mu);
   CK(cudaSetDevice(e->device));
+  trim_keytab(e);
   ThreadCtx c;
   ThreadRecs tr;
   c.eng = e; c.tr = &tr;
@@ -1901,8 +1970,9 @@ int zkb_rsa_verify_batch(zkb_engine* e, const uint8_t* const* key_der, const siz
   DeviceChunk d;
   uint32_t *d_sig = nullptr, *d_dig = nullptr, *d_flags = nullptr;
   RsaItem* d_items[6] = {nullptr};
-  CK(cudaMalloc((void**)&d_sig, std::max<size_t>(16, sigw.size() * 4)));
-  CK(cudaMalloc((void**)&d_dig, n * 32)); CK(cudaMalloc((void**)&d_flags, n * 4));
+  DevTmp tmp;
+  CK(tmp.alloc(&d_sig, std::max<size_t>(16, sigw.size() * 4)));
+  CK(tmp.alloc(&d_dig, n * 32)); CK(tmp.alloc(&d_flags, n * 4));
   CK(cudaMemcpy(d_sig, sigw.data(), sigw.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_dig, dig.data(), n * 32, cudaMemcpyHostToDevice));
   CK(cudaMemset(d_flags, 0, n * 4));
@@ -1910,7 +1980,7 @@ int zkb_rsa_verify_batch(zkb_engine* e, const uint8_t* const* key_der, const siz
   for (int k = 0; k < 6; k++) {
     d.rsa_n[k] = (uint32_t)lists[k].size();
     if (lists[k].empty()) continue;
-    CK(cudaMalloc((void**)&d_items[k], lists[k].size() * sizeof(RsaItem)));
+    CK(tmp.alloc(&d_items[k], lists[k].size() * sizeof(RsaItem)));
     CK(cudaMemcpy(d_items[k], lists[k].data(), lists[k].size() * sizeof(RsaItem), cudaMemcpyHostToDevice));
     d.rsa_items[k] = d_items[k];
   }
@@ -1920,8 +1990,6 @@ int zkb_rsa_verify_batch(zkb_engine* e, const uint8_t* const* key_der, const siz
   std::vector<uint32_t> flags(n);
   CK(cudaMemcpy(flags.data(), d_flags, n * 4, cudaMemcpyDeviceToHost));
   for (size_t i = 0; i < n; i++) if (ok[i] != 2) ok[i] = (flags[i] & ZKB_F_RSA_OK) ? 1 : 0;
-  cudaFree(d_sig); cudaFree(d_dig); cudaFree(d_flags);
-  for (int k = 0; k < 6; k++) if (d_items[k]) cudaFree(d_items[k]);
   return ZKB_OK;
 }
 
@@ -1932,16 +2000,18 @@ int zkb_dfa_scan_batch(zkb_engine* e, const zkb_dfa_view* part, const uint8_t* d
   zkb_regex_set* rs = nullptr;
   int rc = zkb_regex_set_create(e, part, qp ? 0 : 1, qp ? 1 : 0, 1, 1, &rs);
   if (rc) return rc;
+  struct SetGuard { zkb_regex_set* p; ~SetGuard() { zkb_regex_set_destroy(p); } } guard{rs};
   std::lock_guard<std::mutex> lock(e->run_mu);
   CK(cudaSetDevice(e->device));
   std::vector<DfaItem> items(n);
   for (size_t i = 0; i < n; i++) {
-    if (off[i] + len[i] > data_len) { zkb_regex_set_destroy(rs); return ZKB_E_INVALID; }
+    if (off[i] + len[i] > data_len) return ZKB_E_INVALID;
     items[i].hay_off = off[i]; items[i].msg = (uint32_t)i; items[i].out_slot = (uint32_t)i;
   }
   uint8_t* d_arena; DfaItem* d_items; uint4* d_out; uint32_t* d_hlen;
-  CK(cudaMalloc((void**)&d_arena, data_len + 64)); CK(cudaMalloc((void**)&d_items, n * sizeof(DfaItem))); CK(cudaMalloc((void**)&d_out, n * 16));
-  CK(cudaMalloc((void**)&d_hlen, n * 4));
+  DevTmp tmp;
+  CK(tmp.alloc(&d_arena, data_len + 64)); CK(tmp.alloc(&d_items, n * sizeof(DfaItem))); CK(tmp.alloc(&d_out, n * 16));
+  CK(tmp.alloc(&d_hlen, n * 4));
   CK(cudaMemcpy(d_hlen, len, n * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_arena, data, data_len, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_items, items.data(), n * sizeof(DfaItem), cudaMemcpyHostToDevice));
@@ -1952,8 +2022,6 @@ int zkb_dfa_scan_batch(zkb_engine* e, const zkb_dfa_view* part, const uint8_t* d
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s));
   CK(cudaMemcpy(out, d_out, n * 16, cudaMemcpyDeviceToHost));
-  cudaFree(d_arena); cudaFree(d_items); cudaFree(d_out); cudaFree(d_hlen);
-  zkb_regex_set_destroy(rs);
   return ZKB_OK;
 }
 
@@ -1963,7 +2031,8 @@ int zkb_int_pipe_peaks(zkb_engine* e, double out[8]) {
   CK(cudaSetDevice(e->device));
   for (int i = 0; i < 8; i++) out[i] = 0;
   uint32_t* d;
-  CK(cudaMalloc((void**)&d, 64));
+  DevTmp tmp;
+  CK(tmp.alloc(&d, 64));
   cudaStream_t s = e->slots[0].stream;
   const int iters = 4096;
   const unsigned grid = (unsigned)e->sm_count * 8, block = 256;
@@ -1988,7 +2057,6 @@ int zkb_int_pipe_peaks(zkb_engine* e, double out[8]) {
   cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->device);
   out[4] = khz / 1000.0;
   out[5] = e->sm_count;
-  cudaFree(d);
   return ZKB_OK;
 }
 

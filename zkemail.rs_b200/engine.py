@@ -145,8 +145,11 @@ EXPORTED_SYMBOLS = (
     "zkb_dfa_scan_batch", "zkb_int_pipe_peaks", "zkb_host_canonicalize", "zkb_batch_device_flags",
     "zkb_host_register", "zkb_host_unregister", "zkb_engine_last_batch_bytes",
     "zkb_abi_encode_batch", "zkb_abi_decode", "zkb_host_dkim_signatures",
-    "zkb_regex_automata_to_zdf",
+    "zkb_regex_automata_to_zdf", "zkb_engine_set_flags",
 )
+
+# zkb_options.flags / zkb_engine_set_flags (include/zkemail_b200.h)
+OPT_NO_DIRECT, OPT_NO_DEVICE_FRONTEND, OPT_NO_STAGED_FRONTEND, OPT_NO_OVERLAP, OPT_PROFILE = 1, 2, 4, 8, 16
 
 _lib = None
 
@@ -179,6 +182,7 @@ def load_library():
     L.zkb_engine_create.argtypes = [C.POINTER(_Options), C.POINTER(vp)]
     L.zkb_engine_destroy.argtypes = [vp]
     L.zkb_engine_destroy.restype = None
+    L.zkb_engine_set_flags.argtypes = [vp, C.c_uint32]
     L.zkb_regex_set_create.argtypes = [vp, C.POINTER(_DfaView), sz, sz, C.c_int, C.c_int, C.POINTER(vp)]
     L.zkb_regex_set_destroy.argtypes = [vp]
     L.zkb_regex_set_destroy.restype = None
@@ -460,10 +464,11 @@ class Engine:
     """One engine per process and device (zkb_engine)."""
 
     def __init__(self, device: int = 0, host_threads: int = 0, now_unix: int = 0,
-                 chunk_emails: int = 0, rsa_lanes: int = 0):
+                 chunk_emails: int = 0, rsa_lanes: int = 0, flags: int = 0):
         self.lib = load_library()
         self.now_unix = now_unix
-        opt = _Options(device, host_threads, now_unix, chunk_emails, 0, rsa_lanes)
+        self.flags = flags
+        opt = _Options(device, host_threads, now_unix, chunk_emails, flags, rsa_lanes)
         self.handle = C.c_void_p()
         _check(self.lib.zkb_engine_create(C.byref(opt), C.byref(self.handle)), "zkb_engine_create")
 
@@ -477,6 +482,11 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def set_flags(self, flags: int):
+        """Path switches (OPT_* bits); every path gives identical results."""
+        _check(self.lib.zkb_engine_set_flags(self.handle, flags), "zkb_engine_set_flags")
+        self.flags = flags
 
     def last_batch_bytes(self) -> dict:
         h, d, f = C.c_uint64(), C.c_uint64(), C.c_uint64()

@@ -280,10 +280,22 @@ def compile_regex_parts_exact(parts: Sequence[RegexPattern], haystack: bytes, en
             raise RegexError(f"Input doesn't match regex pattern: {part!r}")
         caps: List[str] = []
         if part.capture_indices:
-            rx = re.compile(_py_pattern(part.pattern))
-            m = rx.match(haystack, start, end) if rx.groups else None
+            # MetaRegex::captures searches the WHOLE input (helpers/src/regex.rs:25-27); the only match is the
+            # device's span, so group 0 is that span.  Sub-groups come from Python `re` over a translated pattern,
+            # searched from the span start without an end limit (`$`, `\b` see the same context as in the reference);
+            # a translation whose overall match is not exactly the automaton's span is rejected, never trusted.
+            m = None
+            if any(idx != 0 for idx in part.capture_indices):
+                rx = re.compile(_py_pattern(part.pattern))
+                m = rx.search(haystack, start)
+                if m is None or m.span() != (start, end):
+                    raise RegexError(f"capture groups of {part.pattern!r} cannot be resolved exactly "
+                                     f"(automaton span {(start, end)}, translated pattern {m.span() if m else None})")
             for idx in part.capture_indices:
-                if m is None or idx > rx.groups or m.group(idx) is None:
+                if idx == 0:
+                    caps.append(haystack[start:end].decode("utf-8", errors="replace"))
+                    continue
+                if idx > m.re.groups or m.group(idx) is None:
                     raise RegexError("Capture group not found")
                 caps.append(m.group(idx).decode("utf-8", errors="replace"))
         out.append(CompiledRegex(verify_re=dfa, captures=caps))
