@@ -167,6 +167,13 @@ int zkb_verify_one(zkb_engine *e, const zkb_email_view *email, const zkb_regex_s
 int zkb_batch_prepare(zkb_engine *e, const zkb_email_view *emails, size_t n,
                       const zkb_regex_set *regex, const zkb_email_captures *captures,
                       zkb_batch **out);
+/* Raw-resident form: the RAW messages are made resident (DMA of the registered span, or one staged copy of each
+ * pageable message) and every zkb_batch_run* starts at the device front end: header parsing, preimages, base64, body
+ * canonicalisation, hashing, RSA, DFA scans and the result records all inside the run.  Messages the device declines
+ * are re-run through the host front end by zkb_batch_fetch.  This is the "from raw bytes in HBM" number of bench.py. */
+int zkb_batch_prepare_raw(zkb_engine *e, const zkb_email_view *emails, size_t n,
+                          const zkb_regex_set *regex, const zkb_email_captures *captures,
+                          zkb_batch **out);
 int zkb_batch_run(zkb_batch *b);                 /* enqueue + synchronise */
 int zkb_batch_run_async(zkb_batch *b);           /* enqueue only on the engine stream */
 int zkb_batch_fetch(zkb_batch *b, zkb_result *out);
@@ -182,6 +189,8 @@ int zkb_batch_get_stats(const zkb_batch *b, zkb_batch_stats *out);
 /* CUDA-event time (ms) of the kernels of the last zkb_batch_run, per kernel family, measured on
  * the engine stream: [0]=sha256 [1]=rsa [2]=dfa [3]=bh/finalize [4]=whole run */
 int zkb_batch_last_timing(const zkb_batch *b, float ms[5]);
+/* The same with n <= 8 slots: [5]=device front end + body canonicalisation (raw-resident batches) [6]=result records */
+int zkb_batch_last_timing_ex(const zkb_batch *b, float *ms, size_t n);
 void *zkb_engine_stream(zkb_engine *e);          /* cudaStream_t of the engine */
 /* Bytes the last zkb_verify_batch moved host->device / device->host, and how many of its messages the
  * device front end declined (re-run through the host front end). */
@@ -205,6 +214,60 @@ void zkb_free(void *p);
  * (free with zkb_free).  ZKB_E_REGEX when the blob does not validate — the engine's equivalent of
  * dense::DFA::from_bytes(..).unwrap() panicking (core/src/regex.rs:32-33). */
 int zkb_regex_automata_to_zdf(const uint8_t *wire, size_t wire_len, int reverse, uint8_t **zdf, size_t *zdf_len);
+
+/* ---- multi-GPU ----------------------------------------------------------------------------
+ * verify_email / verify_email_with_regex are pure per-email functions (core/src/circuits.rs:9,31): the batch shards by
+ * email into contiguous, cost-balanced ranges, one engine per device, regex tables replicated.  The only exchange is an
+ * NCCL all-gather of the fixed-size result records (the first 144 bytes of zkb_result + 16 bytes per regex part:
+ * verdict, hashes, match spans), issued by this library on the engine streams.  NCCL is loaded on first use. */
+
+/* Contiguous shards of roughly equal estimated cost: shard k = emails [bounds[k], bounds[k+1]); bounds has n_shards + 1
+ * entries.  resident = 0 balances for the end-to-end path (link bound: bytes), 1 for resident batches (hashing + RSA).
+ * Host-only. */
+int zkb_plan_shards(const zkb_email_view *emails, size_t n, size_t n_shards, int resident, size_t *bounds);
+
+/* (a) ONE process, several devices: one engine and one host thread per device behind a single handle. */
+typedef struct zkb_multi zkb_multi;
+typedef struct zkb_multi_regex zkb_multi_regex;
+typedef struct zkb_multi_batch zkb_multi_batch;
+/* opt->device is ignored; opt->host_threads (0 = all) is split evenly between the devices.  devices == NULL: 0..n-1. */
+int zkb_multi_create(const zkb_options *opt, const int32_t *devices, size_t n_devices, zkb_multi **out);
+void zkb_multi_destroy(zkb_multi *m);
+size_t zkb_multi_devices(const zkb_multi *m);
+zkb_engine *zkb_multi_engine(zkb_multi *m, size_t i);   /* the engine of device i (flags, statistics) */
+int zkb_multi_host_register(zkb_multi *m, const void *p, size_t len);   /* page-locks once, usable by every device */
+int zkb_multi_host_unregister(zkb_multi *m, const void *p);
+int zkb_multi_regex_set_create(zkb_multi *m, const zkb_dfa_view *parts, size_t n_header, size_t n_body,
+                               int header_present, int body_present, zkb_multi_regex **out);
+void zkb_multi_regex_destroy(zkb_multi_regex *r);
+/* zkb_verify_batch over all devices: every device's pipeline writes its range of `out`; no collective is needed for
+ * the host to hold every result. */
+int zkb_multi_verify_batch(zkb_multi *m, const zkb_email_view *emails, size_t n, const zkb_multi_regex *regex,
+                           const zkb_email_captures *captures, zkb_result *out);
+/* Resident form (raw != 0: zkb_batch_prepare_raw on every device). */
+int zkb_multi_batch_prepare(zkb_multi *m, const zkb_email_view *emails, size_t n, const zkb_multi_regex *regex,
+                            const zkb_email_captures *captures, int raw, zkb_multi_batch **out);
+/* Runs every shard's kernels; gather != 0 adds the ncclAllGather of the result records so that every device holds the
+ * whole batch's records.  Returns when all devices are done; *ms_max = slowest device (CUDA events). */
+int zkb_multi_batch_run(zkb_multi_batch *mb, int gather, float *ms_max);
+int zkb_multi_batch_fetch(zkb_multi_batch *mb, zkb_result *out);
+int zkb_multi_batch_bounds(const zkb_multi_batch *mb, size_t *bounds, size_t n);   /* n_devices + 1 entries */
+/* Copies the gathered records as held by device `device_index` to the host, in email order (rec_bytes each). */
+int zkb_multi_batch_gathered(zkb_multi_batch *mb, size_t device_index, uint8_t *host_records, size_t *rec_bytes);
+void zkb_multi_batch_destroy(zkb_multi_batch *mb);
+
+/* (b) one process per device (torchrun-style): rank 0 obtains the id, the caller carries its 128 bytes to the other
+ * processes by any means, every rank creates its communicator (collective call). */
+#define ZKB_COMM_ID_BYTES 128
+typedef struct zkb_comm zkb_comm;
+int zkb_comm_unique_id(uint8_t id[ZKB_COMM_ID_BYTES]);
+int zkb_comm_create(zkb_engine *e, const uint8_t id[ZKB_COMM_ID_BYTES], int rank, int world, zkb_comm **out);
+void zkb_comm_destroy(zkb_comm *c);
+/* Enqueues, on the engine stream behind the kernels of the batch's last zkb_batch_run*, the all-gather of its result
+ * records.  *dev_records: world x *slot_records records of *rec_bytes bytes in this rank's device memory (rank r's
+ * records start at r * slot_records; slot_records = the largest shard, shorter shards are zero padded). */
+int zkb_comm_allgather_records(zkb_comm *c, zkb_batch *b, void **dev_records, size_t *slot_records, size_t *rec_bytes);
+int zkb_comm_rank_records(const zkb_comm *c, uint64_t *counts, size_t n);   /* records held per rank */
 
 /* ---- host-only utility: cfdkim::canonicalize_signed_email (core/src/circuits.rs:34-35,
  * helpers/src/generator.rs:63) ----

@@ -235,3 +235,42 @@ def test_direct_mode_device_canonicalisation(engine):
     for g, e, lab in zip(got2, exp2, labels):
         assert_records_equal(g, e, lab)
     assert int(got2[0]["status"]) == 0
+
+
+def test_raw_resident_batches_redo_the_front_end_every_run(engine):
+    """zkb_batch_prepare_raw: raw messages resident in HBM (staged copies of pageable mail, or the DMA'd registered span);
+    every run starts at the device front end and ends with the device-built result records; messages the device
+    declines are finished by the host front end in fetch.  Records equal the pipeline's and the oracle's."""
+    from tests.util import contiguous_views
+    from zkemail_rs_b200.engine import EmailViews
+    emails, labels = mixed_emails(seed=41, n_pos=60, with_token=True)
+    info = RegexInfo([CompiledRegex(z.compile_regex(r"\r\nsubject:[^\r\n]+\r\n"), None)],
+                     [CompiledRegex(z.compile_regex(r"Transaction ID: [A-Z0-9]+"), ["Transaction ID"])])
+    exp = oracle.verify_batch(emails, info.header_parts, info.body_parts, now=NOW)
+    rs = z.RegexSet(engine, info)
+    try:
+        for registered in (False, True):
+            if registered:
+                buf, views = contiguous_views(emails)
+                engine.register_host(buf)
+            else:
+                views = EmailViews.from_emails(emails)
+            try:
+                for with_caps in (False, True):
+                    pb = engine.prepare(views, rs, with_captures=with_caps, raw=True)
+                    pb.run(); pb.run_async(); pb.run()
+                    got = pb.fetch()
+                    t = pb.timing_ms()
+                    st = pb.stats()
+                    pb.close()
+                    assert t["front_end_canon"] > 0 and st["kernel_launches"] >= 7
+                    pipe = engine.verify_views(views, rs, with_captures=with_caps)
+                    assert got.tobytes() == pipe.tobytes()
+                    if with_caps:
+                        for g, e, lab in zip(got, exp, labels):
+                            assert_records_equal(g, e, lab)
+            finally:
+                if registered:
+                    engine.unregister_host(buf)
+    finally:
+        rs.close()

@@ -15,3 +15,4 @@ from .generator import (  # noqa: F401,E402
     generate_email_with_regex_inputs, parse_dkim_key_record, remove_quoted_printable_soft_breaks,
 )
 from .file import from_serde, read_email_file, read_json_file, to_serde, write_json_file  # noqa: F401,E402
+from .multi import Comm, MultiBatch, MultiEngine, MultiRegexSet, plan_shards, records_to_results  # noqa: F401,E402

@@ -3,6 +3,7 @@
 #ifndef ZKB_HOST_EMU
 #include <cuda_runtime.h>
 #endif
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -74,7 +75,9 @@ struct __align__(16) FeIn {   // host-built, one per message
   uint32_t sig_word_off;      // where this message's signature limbs go (words)
   uint32_t body_msg, pre_msg; // message-table indices of the canonical body / header preimage slots
   uint32_t cand;              // signature-candidate index (bh= words go to cand_bh[8*cand..])
-  uint32_t pad;
+  uint32_t email;             // chunk-local email index (result record slot, assemble.cuh)
+  uint32_t dom_msg, key_msg;  // message-table indices of the from_domain / key hashes
+  uint32_t pad[2];
 };
 struct __align__(16) FeOut {
   uint32_t flags;
@@ -82,6 +85,10 @@ struct __align__(16) FeOut {
   uint32_t pre_len;
   uint32_t bh[8];
 };
+
+// Device-built result records (assemble.cuh): the head of zkb_result followed by one uint4 per regex part
+#define ZKB_REC_HEAD 144            // offsetof(zkb_result, parts)
+#define ZKB_REC_REDO 0x7fffffff     // status of a message the device declined: the host front end decides
 
 // Per-candidate flags written by the device
 #define ZKB_F_RSA_OK 1u

@@ -289,6 +289,8 @@ struct DeviceChunk {   // everything one chunk needs in HBM
   uint32_t* digests = nullptr; uint32_t* cand_flags = nullptr; uint4* dfa_out = nullptr;
   uint32_t M = 0, C = 0, NE = 0, P = 0;
   size_t out_bytes = 0;
+  uint32_t* recs = nullptr; size_t o_recs = 0; uint32_t rec_words = 0;   // device-built result records (assemble.cuh)
+  const FeIn* asm_in = nullptr; const FeOut* asm_fo = nullptr; uint32_t n_asm = 0;   // what the records are built from
   void free() { arena.free(); meta.free(); out.free(); span.free(); }
 };
 
@@ -311,6 +313,7 @@ struct Chunk {  // host view of one chunk
   bool fe = false;
   bool staged = false;   // fe without direct: the host copies each raw message into the staging blocks (pageable callers)
   size_t o_fein = 0;
+  size_t o_asm_in = 0, o_asm_fo = 0;   // host front end: per-email inputs of the record kernel (n_asm = ne)
   const zkb_email_view* views = nullptr;   // the caller's views of this chunk (borrowed for the call)
   size_t upload_bytes = 0;                 // leading part of the meta buffer that is copied host -> device
 };
@@ -347,6 +350,7 @@ struct zkb_engine {
   Slot slots[3];
   std::mutex run_mu;
   std::vector<std::pair<const uint8_t*, size_t>> registered;  // cudaHostRegister'ed caller memory
+  int borrowed_registrations = 0;   // trailing entries of `registered` page-locked by another engine of a zkb_multi (not unregistered here)
   // public keys
   std::mutex key_mu;
   std::unordered_map<std::string, int32_t> key_index;
@@ -355,7 +359,7 @@ struct zkb_engine {
   uint32_t* d_keytab = nullptr;
   size_t d_keytab_cap = 0, d_keytab_n = 0;
   std::atomic<int> live_batches{0};   // resident batches hold key ids: the table is not trimmed while any is alive
-  cudaEvent_t ev[8] = {nullptr};
+  cudaEvent_t ev[10] = {nullptr};
   cudaStream_t aux_stream = nullptr;          // zkb_batch_run_async: hashing of the next chunk beside the RSA of this one
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<cudaEvent_t> ev_pre;            // one per resident chunk index: "pre phase of chunk k done"
@@ -373,8 +377,9 @@ struct zkb_batch {
   std::vector<DeviceChunk*> dev;
   const zkb_email_view* emails = nullptr;       // borrowed until fetch
   const zkb_email_captures* captures = nullptr;  // borrowed until fetch
-  float last_ms[5] = {0, 0, 0, 0, 0};
+  float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // sha256, rsa, dfa, bh check, whole run, front end + canonicalisation, records
   bool ran = false;
+  bool raw = false;   // raw messages resident: every run redoes the device front end and the canonicalisation
 };
 
 namespace {
@@ -861,6 +866,8 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
   for (int k = 0; k < 6; k++) { ch.o_rsa[k] = o; ch.rsa_n[k] = rn[k]; o += align_up((size_t)rn[k] * sizeof(RsaItem), 16); }
   ch.o_dfa = o; o += align_up((size_t)n_dfa * 2 * sizeof(DfaItem), 16);  // header haystack + body haystack per email
   ch.o_fein = o; o += align_up(ch.fe ? (size_t)C * sizeof(FeIn) : 0, 16);
+  ch.o_asm_in = o; o += align_up(ch.fe ? 0 : ne * sizeof(FeIn), 16);
+  ch.o_asm_fo = o; o += align_up(ch.fe ? 0 : ne * sizeof(FeOut), 16);
   if (ch.fe) ch.upload_bytes = o;
   ch.o_cand_bh = o; o += align_up((size_t)C * 32, 16);
   ch.o_sig = o; o += align_up(sig_words * 4, 16);
@@ -923,6 +930,8 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
         fi.sig_word_off = (uint32_t)(sig_base[tid] + cd.sig_off);
         fi.body_msg = t.msg_base + cd.body_msg; fi.pre_msg = t.msg_base + cd.hdr_msg;
         fi.cand = t.cand_base + (uint32_t)j;
+        fi.email = t.fe_emails[j];
+        fi.dom_msg = t.msg_base + er.dom_msg; fi.key_msg = t.msg_base + er.key_msg;
         fin[t.cand_base + j] = fi;
       }
     }
@@ -945,6 +954,34 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
       j++;
     }
   }
+  if (!ch.fe && ne) {
+    // host front end: per-email inputs of the record kernel.  An email decided by exactly one signature candidate
+    // (the common case) gets its record on the device; everything else is marked for the host's resolve_email.
+    FeIn* ain = (FeIn*)(mh + ch.o_asm_in);
+    FeOut* afo = (FeOut*)(mh + ch.o_asm_fo);
+    e->pool->parallel_for(ne, 4096, [&](size_t lo, size_t hi, int) {
+      for (size_t i = lo; i < hi; i++) {
+        const EmailRec& er = ch.emails[i];
+        FeIn fi; FeOut fo;
+        memset(&fi, 0, sizeof fi); memset(&fo, 0, sizeof fo);
+        fi.email = (uint32_t)i;
+        fo.flags = FE_FALLBACK;
+        if (er.status == ZKB_ST_OK && er.n_steps == 1 && (!want_regex || er.canon_rc == 0)) {
+          const ThreadRecs& t = ch.tr[er.tid];
+          const StepRec& st = t.steps[er.first_step];
+          if (st.kind == STEP_CAND && t.cands[st.cand].algo == 1) {
+            const CandRec& cd = t.cands[st.cand];
+            fi.cand = t.cand_base + st.cand;
+            fi.body_msg = t.msg_base + cd.body_msg; fi.pre_msg = t.msg_base + cd.hdr_msg;
+            fi.dom_msg = t.msg_base + er.dom_msg; fi.key_msg = t.msg_base + er.key_msg;
+            fo.flags = (cd.bh_valid ? FE_BH_VALID : 0u) | (cd.sig_state == SIG_SYNTAX ? FE_SIG_SYNTAX : 0u) |
+                       (cd.sig_state == SIG_BADLEN ? FE_SIG_BADLEN : 0u);
+          }
+        }
+        ain[i] = fi; afo[i] = fo;
+      }
+    });
+  }
   memset(&ch.st, 0, sizeof ch.st);
   ch.st.n_emails = ne; ch.st.n_candidates = C; ch.st.n_sha_messages = M;
   ch.st.sha_blocks = sha_blocks; ch.st.sha_bytes = sha_bytes;
@@ -961,12 +998,16 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
   return ZKB_OK;
 }
 
-size_t out_layout(uint32_t M, uint32_t C, size_t ne, size_t P, size_t& o_flags, size_t& o_dfa, size_t n_fe = 0, size_t* o_fe = nullptr) {
+inline uint32_t rec_words_for(size_t P) { return (uint32_t)(36 + 4 * P); }   // 144-byte head + one uint4 per part
+size_t out_layout(uint32_t M, uint32_t C, size_t ne, size_t P, size_t& o_flags, size_t& o_dfa, size_t n_fe = 0, size_t* o_fe = nullptr,
+                  size_t* o_recs = nullptr) {
   size_t o = align_up((size_t)M * 32, 16);
   o_flags = o; o += align_up((size_t)C * 4, 16);
   o_dfa = o; o += ne * P * 16;
   if (o_fe) *o_fe = o;
   o += n_fe * sizeof(FeOut);
+  if (o_recs) *o_recs = o;
+  o += ne * (size_t)rec_words_for(P) * 4;   // one result record per email
   return o + 16;
 }
 
@@ -974,9 +1015,11 @@ size_t out_layout(uint32_t M, uint32_t C, size_t ne, size_t P, size_t& o_flags, 
 int upload_chunk(zkb_engine* e, Chunk& ch, const zkb_regex_set* rs, DeviceChunk& d, PinBuf& pin_meta, cudaStream_t stream) {
   const size_t P = rs ? rs->n_active() : 0;
   if (!d.arena.ensure(ch.arena_bytes) || !d.meta.ensure(ch.meta_bytes)) return ZKB_E_NOMEM;
-  size_t o_flags, o_dfa, o_fe = 0;
-  d.out_bytes = out_layout(ch.M, ch.C, ch.ne, P, o_flags, o_dfa, ch.fe ? ch.C : 0, &o_fe);
+  size_t o_flags, o_dfa, o_fe = 0, o_recs = 0;
+  d.out_bytes = out_layout(ch.M, ch.C, ch.ne, P, o_flags, o_dfa, ch.fe ? ch.C : 0, &o_fe, &o_recs);
   if (!d.out.ensure(d.out_bytes)) return ZKB_E_NOMEM;
+  d.recs = nullptr; d.o_recs = o_recs; d.rec_words = rec_words_for(P);
+  d.asm_in = nullptr; d.asm_fo = nullptr; d.n_asm = 0;
   for (auto& t : ch.tr)
     for (auto& b : t.blocks)
       if (b.used) CK(cudaMemcpyAsync(d.arena.p + b.dev_off, b.p, b.used, cudaMemcpyHostToDevice, stream));
@@ -1001,7 +1044,11 @@ int upload_chunk(zkb_engine* e, Chunk& ch, const zkb_regex_set* rs, DeviceChunk&
     d.canon_rw = (CanonItem*)(d.meta.p + ch.o_canon);
     d.cand_bh_rw = (uint32_t*)(d.meta.p + ch.o_cand_bh);
     d.sig_rw = (uint32_t*)(d.meta.p + ch.o_sig);
+    d.asm_in = d.fe_in; d.asm_fo = d.fe_out; d.n_asm = d.n_fe;
+  } else {
+    d.asm_in = (const FeIn*)(d.meta.p + ch.o_asm_in); d.asm_fo = (const FeOut*)(d.meta.p + ch.o_asm_fo); d.n_asm = (uint32_t)ch.ne;
   }
+  d.recs = (uint32_t*)(d.out.p + o_recs);
   CK(cudaMemsetAsync(d.out.p + o_flags, 0, align_up((size_t)ch.C * 4, 16), stream));
   if (P) CK(cudaMemsetAsync(d.out.p + o_dfa, 0, ch.ne * P * 16, stream));
   d.msg_off = (const uint64_t*)(d.meta.p + ch.o_msg_off);
@@ -1096,6 +1143,20 @@ int launch_chunk(zkb_engine* e, const DeviceChunk& d, const zkb_regex_set* rs, c
     }
   }
   if (ev) CK(cudaEventRecord(ev[4], s));
+  if (rsa && d.n_asm && d.recs) {
+    // result records: needs the RSA flags and (phase 2 runs after the pre phase of the same chunk) the DFA results
+    uint32_t body_mask = 0;
+    if (rs) {
+      uint32_t pi = 0;
+      for (size_t p = 0; p < rs->parts.size(); p++) {
+        if (rs->parts[p].body ? !rs->body_present : !rs->header_present) continue;
+        if (rs->parts[p].body) body_mask |= 1u << pi;
+        pi++;
+      }
+    }
+    launch_assemble(d.asm_in, d.asm_fo, d.n_asm, d.cand_flags, d.digests, d.dfa_out, d.P, body_mask, rs != nullptr, d.recs, d.rec_words, s);
+    nl++;
+  }
   CK(cudaGetLastError());
   if (launches) *launches += nl;
   return ZKB_OK;
@@ -1301,19 +1362,125 @@ bool resolve_email_fe(const zkb_engine* e, const Chunk& ch, size_t i, const uint
   return true;
 }
 
+// Expected-capture check of one part of one email against its haystack rebuilt on the host from the raw message
+// (core/src/regex.rs:41-48; only emails that carry captures pay).  fo: the device front end's record of the message.
+bool captures_hold(const zkb_engine* e, const zkb_email_view& view, const FeOut& fo, bool body, uint32_t start, uint32_t end,
+                   const zkb_email_captures& ec, size_t part, std::vector<uint8_t>& scratch, std::string& s1, std::string& s2) {
+  bool loaded = false;
+  for (size_t q = 0; q < ec.n_caps; q++) {
+    if (ec.caps[q].part != part) continue;
+    if (!loaded) {
+      const uint8_t* raw = view.raw_email;
+      HayView hv;
+      if (body && !(fo.flags & FE_HAS_L)) {
+        scratch.resize((size_t)fo.body_len + 64);
+        size_t cl = (fo.flags & FE_BODY_RELAXED) ? canon_body_relaxed(raw + fo.body_off, fo.body_len, scratch.data())
+                                                 : canon_body_simple(raw + fo.body_off, fo.body_len, scratch.data());
+        hv.p = scratch.data(); hv.n = (uint32_t)cl;
+      } else {
+        uint8_t *hp = nullptr, *bp = nullptr;
+        size_t hl = 0, bl = 0;
+        int detail2 = 0;
+        if (zkb_host_canonicalize(raw, view.raw_email_len, e->now_unix, &hp, &hl, &bp, &bl, &detail2) != ZKB_OK) return false;
+        if (body) scratch.assign(bp, bp + bl);   // l= bodies: the host canonicaliser applies the truncation
+        else scratch.assign(hp, hp + hl);
+        free(hp); free(bp);
+        hv.p = scratch.data(); hv.n = (uint32_t)scratch.size();
+      }
+      cleaned_span(hv, body, start, end, s1);
+      bool ascii = true;
+      for (char ch2 : s1) if (ch2 & 0x80) { ascii = false; break; }
+      if (!ascii) { utf8_lossy((const uint8_t*)s1.data(), s1.size(), s2); s1.swap(s2); }
+      loaded = true;
+    }
+    if (ec.caps[q].len && s1.find(ec.caps[q].s, 0, ec.caps[q].len) == std::string::npos) return false;
+  }
+  return true;
+}
+
+// Device-front-end chunks: the records were built on the device (assemble.cuh); the host copies them into the caller's
+// array, writes the few emails decided before the device (bad key, unsupported key type), collects the messages the
+// device declined and, when the caller passed expected captures, applies the substring checks.
+void resolve_chunk_recs(zkb_engine* e, const Chunk& ch, const uint8_t* outp, size_t o_recs, size_t o_fe, const zkb_regex_set* rs,
+                        const zkb_email_captures* caps, zkb_result* out, std::vector<size_t>* fallback) {
+  const size_t P = rs ? rs->n_active() : 0;
+  const uint32_t rw = rec_words_for(P);
+  const uint32_t* recs = (const uint32_t*)(outp + o_recs);
+  std::mutex fb_mu;
+  e->pool->parallel_for(ch.ne, 1024, [&](size_t lo, size_t hi, int) {
+    std::string s1, s2;
+    std::vector<uint8_t> scratch;
+    std::vector<size_t> local_fb;
+    for (size_t i = lo; i < hi; i++) {
+      zkb_result& res = out[ch.e0 + i];
+      const EmailRec& er = ch.emails[i];
+      if (er.status != ZKB_ST_OK) {
+        memset(&res, 0, rs ? sizeof res : offsetof(zkb_result, parts));
+        res.status = er.status; res.dkim_detail = ZKB_DKIM_NEUTRAL;
+        continue;
+      }
+      const uint32_t* r = recs + i * (size_t)rw;
+      if ((int32_t)r[0] == ZKB_REC_REDO) { local_fb.push_back(ch.e0 + i); continue; }
+      memcpy(&res, r, ZKB_REC_HEAD);
+      if (!rs) continue;
+      memcpy(res.parts, r + 36, P * 16);
+      if (P < ZKB_MAX_PARTS) memset(&res.parts[P], 0, (ZKB_MAX_PARTS - P) * 16);
+      if (!caps || res.n_parts == 0) continue;
+      const zkb_email_captures& ec = caps[ch.e0 + i];
+      if (!ec.n_caps) continue;
+      const ThreadRecs& t = ch.tr[er.tid];
+      const FeOut& fo = ((const FeOut*)(outp + o_fe))[t.cand_base + er.fe_cand];
+      size_t slot = 0;
+      for (size_t p = 0; p < rs->parts.size() && slot < res.n_parts; p++) {
+        const bool body = rs->parts[p].body;
+        if (body ? !rs->body_present : !rs->header_present) continue;
+        if (res.parts[slot].captures_ok &&
+            !captures_hold(e, ch.views[i], fo, body, res.parts[slot].start, res.parts[slot].end, ec, p, scratch, s1, s2)) {
+          // the reference stops at this part (core/src/circuits.rs:45,54): later parts were never evaluated
+          res.parts[slot].captures_ok = 0;
+          res.status = body ? ZKB_ST_REGEX_BODY : ZKB_ST_REGEX_HEADER;
+          res.n_parts = (uint32_t)slot + 1;
+          memset(&res.parts[slot + 1], 0, (ZKB_MAX_PARTS - slot - 1) * 16);
+          break;
+        }
+        slot++;
+      }
+    }
+    if (!local_fb.empty() && fallback) { std::lock_guard<std::mutex> l(fb_mu); fallback->insert(fallback->end(), local_fb.begin(), local_fb.end()); }
+  });
+}
+
 // fallback (optional): chunk-local indices of the messages the device front end declined
 void resolve_chunk(zkb_engine* e, const Chunk& ch, const uint8_t* outp, const zkb_regex_set* rs, const zkb_email_captures* caps,
                    zkb_result* out, std::vector<size_t>* fallback = nullptr) {
   const size_t P = rs ? rs->n_active() : 0;
-  size_t o_flags, o_dfa, o_fe = 0;
-  out_layout(ch.M, ch.C, ch.ne, P, o_flags, o_dfa, ch.fe ? ch.C : 0, &o_fe);
+  size_t o_flags, o_dfa, o_fe = 0, o_recs = 0;
+  out_layout(ch.M, ch.C, ch.ne, P, o_flags, o_dfa, ch.fe ? ch.C : 0, &o_fe, &o_recs);
+  if (ch.fe && ch.C) { resolve_chunk_recs(e, ch, outp, o_recs, o_fe, rs, caps, out, fallback); return; }
   std::mutex fb_mu;
   e->pool->parallel_for(ch.ne, 256, [&](size_t lo, size_t hi, int) {
     std::string s1, s2;
     std::vector<uint8_t> scratch;
     std::vector<size_t> local_fb;
+    const uint32_t rw = rec_words_for(P);
+    const uint32_t* recs = (const uint32_t*)(outp + o_recs);
     for (size_t i = lo; i < hi; i++) {
-      if (!ch.fe) { resolve_email(e, ch, i, outp, o_flags, o_dfa, rs, caps, scratch, out[ch.e0 + i], s1, s2); continue; }
+      if (!ch.fe) {
+        // host front end: emails decided by one signature candidate carry a device-built record; the rest (several
+        // candidates, validation errors, expected captures to check) are resolved here
+        zkb_result& res = out[ch.e0 + i];
+        const uint32_t* r = recs + i * (size_t)rw;
+        if (!caps && ch.emails[i].status == ZKB_ST_OK && (int32_t)r[0] != ZKB_REC_REDO) {
+          memcpy(&res, r, ZKB_REC_HEAD);
+          if (rs) {
+            memcpy(res.parts, r + 36, P * 16);
+            if (P < ZKB_MAX_PARTS) memset(&res.parts[P], 0, (ZKB_MAX_PARTS - P) * 16);
+          }
+          continue;
+        }
+        resolve_email(e, ch, i, outp, o_flags, o_dfa, rs, caps, scratch, res, s1, s2);
+        continue;
+      }
       if (!resolve_email_fe(e, ch, i, outp, o_flags, o_dfa, o_fe, rs, caps, scratch, out[ch.e0 + i], s1, s2)) local_fb.push_back(ch.e0 + i);
     }
     if (!local_fb.empty() && fallback) { std::lock_guard<std::mutex> l(fb_mu); fallback->insert(fallback->end(), local_fb.begin(), local_fb.end()); }
@@ -1414,7 +1581,8 @@ void zkb_engine_destroy(zkb_engine* e) {
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
   if (e->d_keytab) cudaFree(e->d_keytab);
-  for (auto& r : e->registered) cudaHostUnregister(const_cast<uint8_t*>(r.first));
+  if (e->borrowed_registrations == 0)   // engines of a zkb_multi other than the first only borrow the first one's registrations
+    for (auto& r : e->registered) cudaHostUnregister(const_cast<uint8_t*>(r.first));
   e->blocks.release_all();
   delete e->pool;
   delete e;
@@ -1587,9 +1755,16 @@ static int verify_batch_impl(zkb_engine* e, const zkb_email_view* emails, size_t
     rc = launch_chunk(e, s.dev, regex, s.stream, nullptr, nullptr);
     if (rc) break;
     if (prof) CKB(cudaEventRecord(s.k1, s.stream));
-    e->last_h2d += ch.st.h2d_bytes; e->last_d2h += s.dev.out_bytes;
     if (!s.result.ensure(s.dev.out_bytes)) { rc = ZKB_E_NOMEM; break; }
-    CKB(cudaMemcpyAsync(s.result.p, s.dev.out.p, s.dev.out_bytes, cudaMemcpyDeviceToHost, s.stream));
+    {
+      // device front end: the per-email records are the result (the front-end records travel too when expected
+      // captures have to be checked against haystacks rebuilt on the host); host front end: the raw kernel outputs
+      size_t from = 0;
+      if (ch.fe && ch.C) from = captures ? (size_t)((uint8_t*)s.dev.fe_out - s.dev.out.p) : s.dev.o_recs;
+      const size_t nbytes = s.dev.out_bytes - from;
+      e->last_h2d += ch.st.h2d_bytes; e->last_d2h += nbytes;
+      CKB(cudaMemcpyAsync(s.result.p + from, s.dev.out.p + from, nbytes, cudaMemcpyDeviceToHost, s.stream));
+    }
     CKB(cudaEventRecord(s.done, s.stream));
     busy[si] = true;
     t_upload += now_s() - t1;
@@ -1661,8 +1836,8 @@ void zkb_batch_destroy(zkb_batch* b) {
   delete b;
 }
 
-int zkb_batch_prepare(zkb_engine* e, const zkb_email_view* emails, size_t n, const zkb_regex_set* regex,
-                      const zkb_email_captures* captures, zkb_batch** out) {
+static int batch_prepare_impl(zkb_engine* e, const zkb_email_view* emails, size_t n, const zkb_regex_set* regex,
+                              const zkb_email_captures* captures, zkb_batch** out, bool raw) {
   if (!e || !out || (!emails && n)) return ZKB_E_INVALID;
   if (regex && regex->eng != e) return ZKB_E_INVALID;
   *out = nullptr;
@@ -1672,6 +1847,7 @@ int zkb_batch_prepare(zkb_engine* e, const zkb_email_view* emails, size_t n, con
   zkb_batch* b = new zkb_batch();
   e->live_batches.fetch_add(1);
   b->eng = e; b->regex = regex; b->n = n; b->emails = emails; b->captures = captures;
+  b->raw = raw;
   // resident batches: fewer, larger launches (better SM balance).  When the whole batch lies in registered memory
   // (raw bytes are DMA'd, nothing is staged in pinned blocks) a chunk may hold up to 16 GB, so that batches of large
   // messages still give the lane-per-message kernels tens of thousands of lanes per launch (100 KB bodies: 29 K
@@ -1691,12 +1867,19 @@ int zkb_batch_prepare(zkb_engine* e, const zkb_email_view* emails, size_t n, con
     Chunk* ch = new Chunk();
     DeviceChunk* d = new DeviceChunk();
     b->chunks.push_back(ch); b->dev.push_back(d);
-    rc = pack_chunk(e, emails, bounds[k], bounds[k + 1] - bounds[k], regex, *ch, e->slots[0].meta, ctxs, false, max_bytes + ((size_t)1 << 30));
+    rc = pack_chunk(e, emails, bounds[k], bounds[k + 1] - bounds[k], regex, *ch, e->slots[0].meta, ctxs, raw, max_bytes + ((size_t)1 << 30));
     if (rc) break;
     rc = sync_keytab(e, s);
     if (rc) break;
     rc = upload_chunk(e, *ch, regex, *d, e->slots[0].meta, s);
     if (rc) break;
+    if (raw && ch->fe) {
+      // raw-resident form: the raw bytes (registered span or staged copies) stay in HBM and every run starts at the
+      // device front end; nothing is precomputed here
+      if (cudaStreamSynchronize(s) != cudaSuccess) { rc = ZKB_E_CUDA; break; }
+      release_blocks(e, *ch);   // staged copies have reached the arena
+      continue;
+    }
     if (d->n_canon) {
       // resident form: device-side canonicalisation is part of getting the batch resident (it is what
       // the host threads do on the pageable path); zkb_batch_run then launches the verification kernels
@@ -1709,6 +1892,16 @@ int zkb_batch_prepare(zkb_engine* e, const zkb_email_view* emails, size_t n, con
   if (rc) { zkb_batch_destroy(b); return rc; }
   *out = b;
   return ZKB_OK;
+}
+
+int zkb_batch_prepare(zkb_engine* e, const zkb_email_view* emails, size_t n, const zkb_regex_set* regex,
+                      const zkb_email_captures* captures, zkb_batch** out) {
+  return batch_prepare_impl(e, emails, n, regex, captures, out, false);
+}
+
+int zkb_batch_prepare_raw(zkb_engine* e, const zkb_email_view* emails, size_t n, const zkb_regex_set* regex,
+                          const zkb_email_captures* captures, zkb_batch** out) {
+  return batch_prepare_impl(e, emails, n, regex, captures, out, true);
 }
 
 int zkb_batch_run_async(zkb_batch* b) {
@@ -1769,20 +1962,24 @@ int zkb_batch_run(zkb_batch* b) {
   std::lock_guard<std::mutex> lock(e->run_mu);
   CK(cudaSetDevice(e->device));
   cudaStream_t s = e->slots[0].stream;
-  float acc[5] = {0, 0, 0, 0, 0};
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   CK(cudaEventRecord(e->ev[5], s));
   for (auto* d : b->dev) {
     size_t o_flags, o_dfa;
     out_layout(d->M, d->C, d->NE, d->P, o_flags, o_dfa);
     CK(cudaMemsetAsync(d->out.p + o_flags, 0, align_up((size_t)d->C * 4, 16), s));
+    CK(cudaEventRecord(e->ev[7], s));
     int rc = launch_chunk(e, *d, b->regex, s, e->ev, nullptr);
     if (rc) return rc;
-    CK(cudaEventSynchronize(e->ev[4]));
+    CK(cudaEventRecord(e->ev[8], s));
+    CK(cudaEventSynchronize(e->ev[8]));
     float ms;
     CK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1])); acc[0] += ms;   // sha256
     CK(cudaEventElapsedTime(&ms, e->ev[2], e->ev[3])); acc[1] += ms;   // rsa
     CK(cudaEventElapsedTime(&ms, e->ev[3], e->ev[4])); acc[2] += ms;   // dfa
     CK(cudaEventElapsedTime(&ms, e->ev[1], e->ev[2])); acc[3] += ms;   // bh check
+    CK(cudaEventElapsedTime(&ms, e->ev[7], e->ev[0])); acc[5] += ms;   // device front end + body canonicalisation (raw-resident batches)
+    CK(cudaEventElapsedTime(&ms, e->ev[4], e->ev[8])); acc[6] += ms; // result records
   }
   CK(cudaEventRecord(e->ev[6], s));
   CK(cudaEventSynchronize(e->ev[6]));
@@ -1794,7 +1991,13 @@ int zkb_batch_run(zkb_batch* b) {
 
 int zkb_batch_last_timing(const zkb_batch* b, float ms[5]) {
   if (!b || !ms) return ZKB_E_INVALID;
-  memcpy(ms, b->last_ms, sizeof b->last_ms);
+  memcpy(ms, b->last_ms, 5 * sizeof(float));
+  return ZKB_OK;
+}
+
+int zkb_batch_last_timing_ex(const zkb_batch* b, float* ms, size_t n) {
+  if (!b || !ms) return ZKB_E_INVALID;
+  for (size_t i = 0; i < n; i++) ms[i] = i < 8 ? b->last_ms[i] : 0.f;
   return ZKB_OK;
 }
 
@@ -1810,7 +2013,7 @@ int zkb_batch_get_stats(const zkb_batch* b, zkb_batch_stats* out) {
     out->arena_bytes += s.arena_bytes; out->h2d_bytes += s.h2d_bytes;
     out->d2h_bytes += b->dev[i]->out_bytes;
     const DeviceChunk& d = *b->dev[i];
-    uint64_t nl = (d.M ? 1 : 0) + (d.C ? 1 : 0);
+    uint64_t nl = (d.M ? 1 : 0) + (d.C ? 1 : 0) + (d.n_fe ? 1 : 0) + (d.n_asm ? 1 : 0) + (d.n_canon ? 1 : 0);   // + front end, records, canonicalisation
     for (int k = 0; k < 6; k++) nl += d.rsa_n[k] ? 1 : 0;
     if (b->regex && d.n_dfa) nl += b->regex->n_active();
     out->kernel_launches += nl;
@@ -1835,14 +2038,26 @@ int zkb_batch_fetch(zkb_batch* b, zkb_result* out) {
   if (!b->ran) return ZKB_E_INVALID;
   cudaStream_t s = e->slots[0].stream;
   PinBuf& res = e->slots[0].result;
+  std::vector<size_t> fb;
   for (size_t i = 0; i < b->chunks.size(); i++) {
     Chunk& ch = *b->chunks[i];
     DeviceChunk& d = *b->dev[i];
     if (!res.ensure(d.out_bytes)) return ZKB_E_NOMEM;
     CK(cudaMemcpyAsync(res.p, d.out.p, d.out_bytes, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    resolve_chunk(e, ch, res.p, b->regex, b->captures, out);
+    resolve_chunk(e, ch, res.p, b->regex, b->captures, out, b->raw ? &fb : nullptr);
   }
+  if (fb.empty()) return ZKB_OK;
+  // raw-resident batches: messages the device front end declined go through the host front end, as in zkb_verify_batch
+  std::sort(fb.begin(), fb.end());
+  std::vector<zkb_email_view> v2(fb.size());
+  std::vector<zkb_email_captures> c2(b->captures ? fb.size() : 0);
+  std::vector<zkb_result> r2(fb.size());
+  for (size_t i = 0; i < fb.size(); i++) { v2[i] = b->emails[fb[i]]; if (b->captures) c2[i] = b->captures[fb[i]]; }
+  int rc = verify_batch_impl(e, v2.data(), v2.size(), b->regex, b->captures ? c2.data() : nullptr, r2.data(), false, nullptr);
+  if (rc) return rc;
+  const size_t rec_bytes = b->regex ? sizeof(zkb_result) : offsetof(zkb_result, parts);
+  for (size_t i = 0; i < fb.size(); i++) memcpy(&out[fb[i]], &r2[i], rec_bytes);
   return ZKB_OK;
 }
 
@@ -2061,3 +2276,5 @@ int zkb_int_pipe_peaks(zkb_engine* e, double out[8]) {
 }
 
 }  // extern "C"
+
+#include "engine_multi.inc"

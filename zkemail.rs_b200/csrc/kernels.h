@@ -32,6 +32,9 @@ void launch_canon_body(const uint8_t* span, const CanonItem* items, uint32_t n, 
                        uint32_t* msg_len, cudaStream_t s);
 void launch_frontend(const uint8_t* span, const FeIn* in, uint32_t n, uint8_t* arena, const uint64_t* msg_off, uint32_t* msg_len,
                      uint32_t* sig_arena, uint32_t* cand_bh, CanonItem* canon, FeOut* out, bool allow_skip, long long now, cudaStream_t s);
+// per-email result records (assemble.cuh); rec_words = record stride in 32-bit words
+void launch_assemble(const FeIn* in, const FeOut* fo, uint32_t n, const uint32_t* cand_flags, const uint32_t* digests, const uint4* dfa_out,
+                     uint32_t P, uint32_t body_mask, bool have_regex, uint32_t* recs, uint32_t rec_words, cudaStream_t s);
 void launch_int_peak(int kind, unsigned grid, unsigned block, uint32_t* out, uint32_t seed, int iters, cudaStream_t s);
 
 }  // namespace zkb

@@ -145,7 +145,12 @@ EXPORTED_SYMBOLS = (
     "zkb_dfa_scan_batch", "zkb_int_pipe_peaks", "zkb_host_canonicalize", "zkb_batch_device_flags",
     "zkb_host_register", "zkb_host_unregister", "zkb_engine_last_batch_bytes",
     "zkb_abi_encode_batch", "zkb_abi_decode", "zkb_host_dkim_signatures",
-    "zkb_regex_automata_to_zdf", "zkb_engine_set_flags",
+    "zkb_regex_automata_to_zdf", "zkb_engine_set_flags", "zkb_batch_prepare_raw", "zkb_batch_last_timing_ex",
+    "zkb_plan_shards", "zkb_multi_create", "zkb_multi_destroy", "zkb_multi_devices", "zkb_multi_engine", "zkb_multi_host_register",
+    "zkb_multi_host_unregister", "zkb_multi_regex_set_create", "zkb_multi_regex_destroy", "zkb_multi_verify_batch",
+    "zkb_multi_batch_prepare", "zkb_multi_batch_run", "zkb_multi_batch_fetch", "zkb_multi_batch_bounds", "zkb_multi_batch_gathered",
+    "zkb_multi_batch_destroy", "zkb_comm_unique_id", "zkb_comm_create", "zkb_comm_destroy", "zkb_comm_allgather_records",
+    "zkb_comm_rank_records",
 )
 
 # zkb_options.flags / zkb_engine_set_flags (include/zkemail_b200.h)
@@ -189,6 +194,8 @@ def load_library():
     L.zkb_verify_batch.argtypes = [vp, vp, sz, vp, vp, vp]
     L.zkb_verify_one.argtypes = [vp, vp, vp, vp, vp]
     L.zkb_batch_prepare.argtypes = [vp, vp, sz, vp, vp, C.POINTER(vp)]
+    L.zkb_batch_prepare_raw.argtypes = [vp, vp, sz, vp, vp, C.POINTER(vp)]
+    L.zkb_batch_last_timing_ex.argtypes = [vp, C.POINTER(C.c_float), sz]
     L.zkb_batch_run.argtypes = [vp]
     L.zkb_batch_run_async.argtypes = [vp]
     L.zkb_batch_fetch.argtypes = [vp, vp]
@@ -408,13 +415,13 @@ class RegexSet:
 class PreparedBatch:
     """A batch packed and resident in HBM (zkb_batch): run() launches only the kernels."""
 
-    def __init__(self, engine: "Engine", views: EmailViews, regex: Optional[RegexSet], caps):
-        self.engine, self.views, self.regex, self._caps = engine, views, regex, caps
+    def __init__(self, engine: "Engine", views: EmailViews, regex: Optional[RegexSet], caps, raw: bool = False):
+        self.engine, self.views, self.regex, self._caps, self.raw = engine, views, regex, caps, raw
         self.handle = C.c_void_p()
         cap_ptr = caps[0].ctypes.data if caps and caps[0] is not None else None
-        _check(engine.lib.zkb_batch_prepare(engine.handle, views.ptr, views.n,
-                                            regex.handle if regex else None, cap_ptr,
-                                            C.byref(self.handle)), "zkb_batch_prepare")
+        fn = engine.lib.zkb_batch_prepare_raw if raw else engine.lib.zkb_batch_prepare
+        _check(fn(engine.handle, views.ptr, views.n, regex.handle if regex else None, cap_ptr,
+                  C.byref(self.handle)), "zkb_batch_prepare_raw" if raw else "zkb_batch_prepare")
 
     def run(self):
         _check(self.engine.lib.zkb_batch_run(self.handle), "zkb_batch_run")
@@ -423,9 +430,9 @@ class PreparedBatch:
         _check(self.engine.lib.zkb_batch_run_async(self.handle), "zkb_batch_run_async")
 
     def timing_ms(self) -> dict:
-        t = (C.c_float * 5)()
-        _check(self.engine.lib.zkb_batch_last_timing(self.handle, C.byref(t)), "zkb_batch_last_timing")
-        return {"sha256": t[0], "rsa": t[1], "dfa": t[2], "bh_check": t[3], "total": t[4]}
+        t = (C.c_float * 8)()
+        _check(self.engine.lib.zkb_batch_last_timing_ex(self.handle, t, 8), "zkb_batch_last_timing_ex")
+        return {"sha256": t[0], "rsa": t[1], "dfa": t[2], "bh_check": t[3], "total": t[4], "front_end_canon": t[5], "records": t[6]}
 
     def stats(self) -> dict:
         s = BatchStats()
@@ -521,9 +528,12 @@ class Engine:
         finally:
             rs.close()
 
-    def prepare(self, views: EmailViews, regex: Optional[RegexSet] = None, with_captures: bool = True) -> PreparedBatch:
+    def prepare(self, views: EmailViews, regex: Optional[RegexSet] = None, with_captures: bool = True,
+                raw: bool = False) -> PreparedBatch:
+        """Resident batch.  raw=False: canonical bytes packed in HBM, run() = hashing + RSA + DFA scans.  raw=True: the raw
+        messages are resident and run() starts at the device front end (zkb_batch_prepare_raw)."""
         caps = regex.captures_for(views.n) if (regex and with_captures) else (None, None)
-        return PreparedBatch(self, views, regex, caps)
+        return PreparedBatch(self, views, regex, caps, raw)
 
     # ---- the reference's single-email call shape ------------------------------------------
     def verify_email(self, email: Email) -> EmailVerifierOutput:

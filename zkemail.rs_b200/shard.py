@@ -70,3 +70,28 @@ def verify_batch_sharded(engine, emails, regex_info=None, device=None):
     mine = emails[lo:hi]
     local = engine.verify_with_regex_batch(mine, regex_info) if regex_info is not None else engine.verify_batch(mine)
     return all_gather_records(local, n, rank, world, device=device)
+
+
+def gather_record_slots(local: np.ndarray, rank: int, world: int, device=None):
+    """The layout of zkb_comm_allgather_records (csrc/engine_multi.inc) on any torch.distributed backend: the per-rank
+    record counts are exchanged first, every rank's records go into a slot of `slot` = max count records (zero padded),
+    slots are all-gathered; returns (gathered [world, slot, width] uint8, counts).  Used by the gloo tests of the
+    multi-GPU host logic; on the GPU box the library issues the same exchange with NCCL itself."""
+    import torch
+    import torch.distributed as dist
+    width = local.dtype.itemsize
+    cnt = torch.tensor([len(local)], dtype=torch.int64)
+    if device is not None:
+        cnt = cnt.to(device)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt)
+    counts = [int(c.item()) for c in cnts]
+    slot = max(counts)
+    buf = np.zeros((slot, width), dtype=np.uint8)
+    buf[: len(local)] = local.view(np.uint8).reshape(len(local), width)
+    t = torch.from_numpy(buf)
+    if device is not None:
+        t = t.to(device)
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t)
+    return np.stack([o.cpu().numpy() for o in outs]), counts
