@@ -381,12 +381,15 @@ def main():
                                   + (" + DFA scans" if main_regex else "") + " + result records"}
 
     # ---- end to end through the C ABI with host buffers ----
+    from zkemail_rs_b200.engine import RESULT_DTYPE
+    out_buf = np.zeros(n_emails, dtype=RESULT_DTYPE)   # the caller's result array, reused across calls like its input buffers
+
     def timed_e2e(vw, rs, label):
-        eng.verify_views(vw, rs, with_captures=False)   # one untimed call (staging buffers allocated)
+        eng.verify_views(vw, rs, with_captures=False, out=out_buf)   # one untimed call (staging buffers allocated)
         barrier()
         t0 = time.perf_counter()
         for _ in range(K):
-            r2 = eng.verify_views(vw, rs, with_captures=False)
+            r2 = eng.verify_views(vw, rs, with_captures=False, out=out_buf)
             if dist is not None:   # every rank learns every shard's verdicts: bitmap all-gather inside the step
                 bits = torch.from_numpy(np.packbits(r2["status"] == 0)).to(dev)
                 allb = torch.empty(bits.numel() * world, dtype=torch.uint8, device=dev)

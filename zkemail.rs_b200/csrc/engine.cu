@@ -807,6 +807,11 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
       if (lo >= ne) break;
       size_t hi = std::min(ne, lo + grain);
       for (size_t i = lo; i < hi; i++) {
+        if (ch.staged && i + 1 < hi) {   // the next message is a cold heap allocation: start pulling its first lines in
+          const uint8_t* nx = emails[e0 + i + 1].raw_email;
+          const size_t nl = std::min<size_t>(emails[e0 + i + 1].raw_email_len, 512);
+          for (size_t o = 0; o < nl; o += 64) __builtin_prefetch(nx + o, 0, 0);
+        }
         if (ch.fe) process_email_fe(c, emails[e0 + i], (uint32_t)i, tid, ch.emails[i]);
         else process_email(c, emails[e0 + i], want_regex, tid, ch.emails[i]);
         if (c.oom) { oom = 1; return; }
@@ -936,23 +941,43 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
       }
     }
   });
-  // DFA items: for each email with haystacks, slot 2*j = header preimage, 2*j+1 = canonical body
+  // DFA items: for each email with haystacks, slot 2*j = header preimage, 2*j+1 = canonical body (j = rank of the
+  // email among those with haystacks: counted per grain, prefix-summed, filled in parallel)
   uint64_t dfa_bytes = 0;
   if (P) {
     DfaItem* items = (DfaItem*)(mh + ch.o_dfa);
-    uint32_t j = 0;
-    for (size_t i = 0; i < ne; i++) {
-      EmailRec& er = ch.emails[i];
-      if (er.status != ZKB_ST_OK || er.canon_rc != 0) continue;
-      ThreadRecs& t = ch.tr[er.tid];
-      const CandRec& cd = t.cands[er.canon_cand];
-      const MsgRec& hm = t.msgs[cd.hdr_msg];
-      const MsgRec& bm = t.msgs[cd.body_msg];
-      items[2 * j].hay_off = hm.goff; items[2 * j].msg = t.msg_base + cd.hdr_msg; items[2 * j].out_slot = (uint32_t)i;
-      items[2 * j + 1].hay_off = bm.goff; items[2 * j + 1].msg = t.msg_base + cd.body_msg; items[2 * j + 1].out_slot = (uint32_t)i;
-      dfa_bytes += (uint64_t)hm.len * (rs->header_present ? rs->n_header : 0) + (uint64_t)bm.len * (rs->body_present ? rs->n_body : 0);
-      j++;
-    }
+    const size_t G = 4096, ng = (ne + G - 1) / G;
+    std::vector<uint32_t> gstart(ng + 1, 0);
+    e->pool->parallel_for(ng, 1, [&](size_t lo, size_t hi, int) {
+      for (size_t g = lo; g < hi; g++) {
+        uint32_t c = 0;
+        for (size_t i = g * G; i < std::min(ne, (g + 1) * G); i++) c += (ch.emails[i].status == ZKB_ST_OK && ch.emails[i].canon_rc == 0) ? 1u : 0u;
+        gstart[g + 1] = c;
+      }
+    });
+    for (size_t g = 0; g < ng; g++) gstart[g + 1] += gstart[g];
+    std::atomic<uint64_t> bytes_acc{0};
+    const uint64_t nh_parts = rs->header_present ? rs->n_header : 0, nb_parts = rs->body_present ? rs->n_body : 0;
+    e->pool->parallel_for(ng, 1, [&](size_t lo, size_t hi, int) {
+      uint64_t local = 0;
+      for (size_t g = lo; g < hi; g++) {
+        uint32_t j = gstart[g];
+        for (size_t i = g * G; i < std::min(ne, (g + 1) * G); i++) {
+          EmailRec& er = ch.emails[i];
+          if (er.status != ZKB_ST_OK || er.canon_rc != 0) continue;
+          ThreadRecs& t = ch.tr[er.tid];
+          const CandRec& cd = t.cands[er.canon_cand];
+          const MsgRec& hm = t.msgs[cd.hdr_msg];
+          const MsgRec& bm = t.msgs[cd.body_msg];
+          items[2 * j].hay_off = hm.goff; items[2 * j].msg = t.msg_base + cd.hdr_msg; items[2 * j].out_slot = (uint32_t)i;
+          items[2 * j + 1].hay_off = bm.goff; items[2 * j + 1].msg = t.msg_base + cd.body_msg; items[2 * j + 1].out_slot = (uint32_t)i;
+          local += (uint64_t)hm.len * nh_parts + (uint64_t)bm.len * nb_parts;
+          j++;
+        }
+      }
+      bytes_acc.fetch_add(local);
+    });
+    dfa_bytes = bytes_acc.load();
   }
   if (!ch.fe && ne) {
     // host front end: per-email inputs of the record kernel.  An email decided by exactly one signature candidate

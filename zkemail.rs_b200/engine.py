@@ -508,8 +508,12 @@ class Engine:
         _check(self.lib.zkb_host_unregister(self.handle, array.ctypes.data), "zkb_host_unregister")
 
     # ---- batch entry points -------------------------------------------------------------
-    def verify_views(self, views: EmailViews, regex: Optional[RegexSet] = None, with_captures: bool = True) -> np.ndarray:
-        out = np.zeros(views.n, dtype=RESULT_DTYPE)
+    def verify_views(self, views: EmailViews, regex: Optional[RegexSet] = None, with_captures: bool = True,
+                     out: Optional[np.ndarray] = None) -> np.ndarray:
+        """zkb_verify_batch.  `out`: caller-owned result array to reuse (RESULT_DTYPE, views.n records)."""
+        if out is None:
+            out = np.zeros(views.n, dtype=RESULT_DTYPE)
+        assert out.dtype == RESULT_DTYPE and len(out) == views.n and out.flags.c_contiguous
         caps = regex.captures_for(views.n) if (regex and with_captures) else (None, None)
         cap_ptr = caps[0].ctypes.data if caps[0] is not None else None
         _check(self.lib.zkb_verify_batch(self.handle, views.ptr, views.n, regex.handle if regex else None,
