@@ -12,6 +12,7 @@
 #include "../../zkemail.rs_b200/csrc/canon.cuh"
 #include "../../zkemail.rs_b200/csrc/dkim_host.hpp"
 #include "../../zkemail.rs_b200/csrc/frontend.cuh"
+#include "../../zkemail.rs_b200/csrc/frontend_warp.cuh"
 // dfa.cuh added below once rewritten
 
 using namespace zkb;
@@ -135,25 +136,17 @@ void emu_canon_body(const uint8_t* span, const uint64_t* off, const uint32_t* le
   emu::launch((n + block - 1) / block, block, [&]() { canon_body_kernel(span, items.data(), n, arena, slot_off, out_len); });
 }
 
-// Device front end (frontend.cuh: fe_process) against the host front end (dkim_host.hpp) on one message.
+// What the device front end produced for one message, checked against the host front end (dkim_host.hpp).
 // returns 0 = the device path declines (fallback), 1 = live and identical to the host, 2 = both report a
 // mail parse error, negative = MISMATCH (code tells which field).
-int emu_fe_compare(const uint8_t* raw_in, uint32_t n, const uint8_t* dom, uint32_t dom_len, uint32_t k, uint32_t limbs, int allow_skip) {
-  // the device reads whole aligned 16-byte blocks: give it the message at an odd offset inside a padded buffer
-  std::vector<uint8_t> padded((size_t)n + 96, 0x3B);
-  uint8_t* raw = padded.data() + 16 + ((16 - ((uintptr_t)padded.data() & 15)) & 15) + 5;
-  memcpy(raw, raw_in, n);
-  std::vector<uint8_t> pre(FE_PRE_CAP + 64, 0xEE);
-  std::vector<uint32_t> sigw(limbs, 0xDEADBEEFu);
-  FeOut fo;
-  uint32_t body_l = 0;
-  fe_process(raw, n, dom, dom_len, k, limbs, pre.data(), sigw.data(), fo, body_l, allow_skip != 0, 1);
+static int fe_check_against_host(const uint8_t* raw, uint32_t n, const uint8_t* dom, uint32_t dom_len, uint32_t k, uint32_t limbs, int allow_skip,
+                                 const FeOut& fo, const std::vector<uint8_t>& pre, const std::vector<uint32_t>& sigw, uint32_t body_l) {
   std::vector<HeaderField> hs;
   size_t body_off = 0;
   const bool parsed = parse_headers(raw, n, hs, body_off);
   if (fo.flags & FE_MAIL_PARSE) return parsed ? -1 : 2;
-  if (!parsed) return -2;
   if (fo.flags & FE_FALLBACK) return 0;
+  if (!parsed) return -2;
   // live on the device: the host must reach the cryptographic checks with the same bytes
   DkimSig sig;
   std::string scratch;
@@ -209,6 +202,49 @@ int emu_fe_compare(const uint8_t* raw_in, uint32_t n, const uint8_t* dom, uint32
     for (uint32_t x : sigw) if (x != 0) return -17;
   }
   return 1;
+}
+
+// the device reads whole aligned 16-byte blocks: give it the message at an odd offset inside a padded buffer
+static uint8_t* fe_place(std::vector<uint8_t>& padded, const uint8_t* raw_in, uint32_t n) {
+  padded.assign((size_t)n + 96, 0x3B);
+  uint8_t* raw = padded.data() + 16 + ((16 - ((uintptr_t)padded.data() & 15)) & 15) + 5;
+  memcpy(raw, raw_in, n);
+  return raw;
+}
+
+// Scalar device front end (frontend.cuh: fe_process) against the host front end on one message.
+int emu_fe_compare(const uint8_t* raw_in, uint32_t n, const uint8_t* dom, uint32_t dom_len, uint32_t k, uint32_t limbs, int allow_skip) {
+  std::vector<uint8_t> padded;
+  uint8_t* raw = fe_place(padded, raw_in, n);
+  std::vector<uint8_t> pre(FE_PRE_CAP + 64, 0xEE);
+  std::vector<uint32_t> sigw(limbs, 0xDEADBEEFu);
+  FeOut fo;
+  uint32_t body_l = 0;
+  fe_process(raw, n, dom, dom_len, k, limbs, pre.data(), sigw.data(), fo, body_l, allow_skip != 0, 1);
+  return fe_check_against_host(raw, n, dom, dom_len, k, limbs, allow_skip, fo, pre, sigw, body_l);
+}
+
+// Warp-cooperative device front end (frontend_warp.cuh: fe_process_warp, 32 emulated lanes) against the host front
+// end.  *scalar_rc receives the scalar twin's verdict on the same message (the warp form may decline more, never less
+// exactly: a message it accepts must compare equal to the host).
+int emu_fe_compare_warp(const uint8_t* raw_in, uint32_t n, const uint8_t* dom, uint32_t dom_len, uint32_t k, uint32_t limbs, int allow_skip,
+                        int* scalar_rc) {
+  std::vector<uint8_t> padded;
+  uint8_t* raw = fe_place(padded, raw_in, n);
+  std::vector<uint8_t> pre(FE_PRE_CAP + 64, 0xEE);
+  std::vector<uint32_t> sigw(limbs, 0xDEADBEEFu);
+  FeOut fo;
+  memset(&fo, 0, sizeof fo);
+  uint32_t body_l = 0;
+  emu::launch(1, 32, [&]() {
+    static FeWarpSmem sm;
+    FeOut mine;
+    uint32_t bl = 0;
+    fe_process_warp(&sm, raw, n, dom, dom_len, k, limbs, pre.data(), sigw.data(), mine, bl, allow_skip != 0, 1);
+    if ((threadIdx.x & 31) == 0) { fo = mine; body_l = bl; }
+  });
+  if (scalar_rc) *scalar_rc = emu_fe_compare(raw_in, n, dom, dom_len, k, limbs, allow_skip);
+  return fe_check_against_host(raw, n, dom, dom_len, k, limbs, allow_skip, fo, pre, sigw, body_l);
 }
 
 }  // extern "C"

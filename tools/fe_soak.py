@@ -1,5 +1,5 @@
 """CPU soak of the device front end under emulation (no GPU needed): tools/fuzz_frontend.py mail through the
-frontend.cuh source (tests/emu) against the host front end, with and without foreign-signature skipping.
+frontend.cuh / frontend_warp.cuh sources (tests/emu) against the host front end, with and without foreign-signature skipping.
 
     python tools/fe_soak.py [seed] [n_emails]
 
@@ -24,16 +24,22 @@ def main():
     from tests import emu
     lib = emu.lib()
     hist, bad = collections.Counter(), 0
+    import ctypes as C
+    whist = collections.Counter()
     for e in fz.build(n, seed):
         dom = e.from_domain.encode()
         for skip in (0, 1):
-            r = lib.emu_fe_compare(e.raw_email, len(e.raw_email), dom, len(dom), 128, 32, skip)
+            sc = C.c_int(-99)
+            # the warp-cooperative kernel source (32 emulated lanes) and, through it, the scalar twin
+            rw = lib.emu_fe_compare_warp(e.raw_email, len(e.raw_email), dom, len(dom), 128, 32, skip, C.byref(sc))
+            r = sc.value
             hist[(skip, r)] += 1
-            if r < 0:
+            whist[(skip, rw)] += 1
+            if r < 0 or rw < 0 or (rw == 1 and r == 2) or (rw == 2 and r == 1):
                 bad += 1
                 if bad < 6:
-                    print("MISMATCH", r, skip, e.from_domain, e.raw_email[:500], file=sys.stderr)
-    print(f"fe_soak seed {seed}: {dict(sorted(hist.items()))} mismatches {bad}")
+                    print("MISMATCH scalar", r, "warp", rw, skip, e.from_domain, e.raw_email[:500], file=sys.stderr)
+    print(f"fe_soak seed {seed}: scalar {dict(sorted(hist.items()))} warp {dict(sorted(whist.items()))} mismatches {bad}")
     return 1 if bad else 0
 
 

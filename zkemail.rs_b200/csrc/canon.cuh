@@ -13,11 +13,21 @@
 // Mapping: lane = body.  The relaxed transform is a forward transducer with one byte of look-ahead
 // (a pending SP is dropped iff the next two bytes are CR LF), so a lane streams its body with
 // aligned 16-byte loads and writes the output through a 64-bit shift register (one 8-byte store per
-// 8 output bytes).  No data-dependent branches in the byte loop: the lanes of a warp stay converged.
+// 8 output bytes).  A 16-byte block that needs no editing — no TAB, no SP followed by SP or CR, previous
+// byte not WSP; found with a handful of SWAR byte-mask operations — is passed through as two 8-byte
+// emits (~2.5 instructions per byte); only blocks that contain something to canonicalise, and the two
+// boundary blocks, take the byte loop (~25 instructions per byte, branch-free inside).  Simple
+// canonicalisation is the pass-through for every full block.
 #pragma once
 #include "common.cuh"
 
 namespace zkb {
+
+// 0x80 in every byte of x that equals c (exact, no borrow artefacts)
+__device__ __forceinline__ uint32_t canon_eq_mask(uint32_t x, uint32_t c) {
+  const uint32_t t = x ^ (c * 0x01010101u);
+  return ~(((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t) & 0x80808080u;
+}
 
 struct CanonOut {
   uint8_t* out;
@@ -29,6 +39,16 @@ struct CanonOut {
       o++;
       if ((o & 7u) == 0) { *reinterpret_cast<uint64_t*>(out + o - 8) = acc; acc = 0; }
     }
+  }
+  // eight bytes at once (the pass-through path)
+  __device__ __forceinline__ void emit8(uint64_t q) {
+    const uint32_t k = (o & 7u) * 8u;
+    if (k == 0) { *reinterpret_cast<uint64_t*>(out + o) = q; }
+    else {
+      *reinterpret_cast<uint64_t*>(out + (o & ~7u)) = acc | (q << k);
+      acc = q >> (64u - k);
+    }
+    o += 8;
   }
   __device__ __forceinline__ void flush() {
     for (uint32_t k = 0; k < (o & 7u); k++) out[(o & ~7u) + k] = (uint8_t)(acc >> (8 * k));
@@ -57,6 +77,31 @@ canon_body_kernel(const uint8_t* __restrict__ span, const CanonItem* __restrict_
   for (uint32_t base = 0; base < total; base += 16) {
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(a0 + base));
     const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+    // pass-through test: a full block behind a pending non-WSP byte, with nothing to edit inside
+    bool pass = base >= lead && base + 16 <= total && prev >= 0;
+    if (pass && relaxed) {
+      pass = !pending_sp && prev != ' ' && prev != '\t';
+      uint32_t sp[4], cr[4], tab = 0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) { sp[q] = canon_eq_mask(w4[q], ' '); cr[q] = canon_eq_mask(w4[q], '\r'); tab |= canon_eq_mask(w4[q], '\t'); }
+      uint32_t bad = tab;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        // flags of byte i + 1 aligned at byte i (the successor of byte 15 is judged with the next block: that byte
+        // becomes `prev`, and a WSP `prev` sends the next block through the byte loop)
+        const uint32_t nx = ((sp[q] | cr[q]) >> 8) | (q < 3 ? (sp[q + 1] | cr[q + 1]) << 24 : 0u);
+        bad |= sp[q] & nx;
+      }
+      pass = pass && bad == 0;
+    }
+    if (pass) {
+      const uint32_t p = (uint32_t)prev;
+      const uint32_t o0 = p | (v.x << 8), o1 = __funnelshift_l(v.x, v.y, 8), o2 = __funnelshift_l(v.y, v.z, 8), o3 = __funnelshift_l(v.z, v.w, 8);
+      w.emit8((uint64_t)o0 | ((uint64_t)o1 << 32));
+      w.emit8((uint64_t)o2 | ((uint64_t)o3 << 32));
+      prev = (int)(v.w >> 24);
+      continue;
+    }
 #pragma unroll
     for (int k = 0; k < 16; k++) {
       const uint32_t pos = base + (uint32_t)k;
