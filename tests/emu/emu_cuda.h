@@ -135,6 +135,16 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
   for (int i = 0; i < 32; i++) r |= (c.warp->box[ph][i] & 1u) << i;
   return r;
 }
+static inline unsigned __reduce_or_sync(unsigned, unsigned v) {
+  emu::Ctx& c = emu::ctx;
+  int ph = c.phase;
+  c.phase ^= 1;
+  c.warp->box[ph][c.lane] = v;
+  c.warp->bar.arrive_and_wait();
+  unsigned r = 0;
+  for (int i = 0; i < 32; i++) r |= c.warp->box[ph][i];
+  return r;
+}
 static inline void __syncthreads() { emu::ctx.block->bar.arrive_and_wait(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::ctx.warp->bar.arrive_and_wait(); emu::ctx.phase ^= 0; }
 

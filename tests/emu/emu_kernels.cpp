@@ -27,6 +27,15 @@ static void run_rsa(const uint32_t* sig_arena, const RsaItem* items, uint32_t n_
   });
 }
 
+static void run_rsa_sqr(const uint32_t* sig_arena, const RsaItem* items, uint32_t n_items,
+                        const uint32_t* keytab, const uint32_t* digests, uint32_t* flags) {
+  const unsigned block = 64;
+  unsigned threads = n_items * 4;
+  emu::launch((threads + block - 1) / block, block, [&]() {
+    rsa_verify_kernel<64, 4, false, true>(sig_arena, items, n_items, keytab, digests, flags);
+  });
+}
+
 extern "C" {
 
 void emu_sha256_batch(const uint8_t* arena, const uint64_t* off, const uint32_t* len,
@@ -55,6 +64,7 @@ int emu_rsa_verify(int limbs, int T, int generic, const uint32_t* sig_arena, con
                    uint32_t n_items, const uint32_t* keytab, const uint32_t* digests,
                    uint32_t* flags) {
   const RsaItem* it = (const RsaItem*)items;
+  if (limbs == 64 && T == 104 && !generic) { run_rsa_sqr(sig_arena, it, n_items, keytab, digests, flags); return 0; }   // T = 104: the squaring variant
 #define CASE(LB, TT)                                                                        \
   if (limbs == LB && T == TT) {                                                             \
     if (generic) run_rsa<LB, TT, true>(sig_arena, it, n_items, keytab, digests, flags);     \
@@ -133,7 +143,8 @@ void emu_canon_body(const uint8_t* span, const uint64_t* off, const uint32_t* le
     items[i].raw_off = off[i]; items[i].raw_len = len[i]; items[i].msg = i; items[i].flags = flags[i]; items[i].l = lval[i];
   }
   const unsigned block = 128;
-  emu::launch((n + block - 1) / block, block, [&]() { canon_body_kernel(span, items.data(), n, arena, slot_off, out_len); });
+  if (getenv("ZKB_EMU_CANON_UNSTAGED")) emu::launch((n + block - 1) / block, block, [&]() { canon_body_kernel(span, items.data(), n, arena, slot_off, out_len); });
+  else emu::launch((n + block - 1) / block, block, [&]() { canon_body_staged_kernel(span, items.data(), n, arena, slot_off, out_len); });
 }
 
 // What the device front end produced for one message, checked against the host front end (dkim_host.hpp).
@@ -181,7 +192,13 @@ static int fe_check_against_host(const uint8_t* raw, uint32_t n, const uint8_t* 
   if ((size_t)(b - raw) != fo.body_off || bl != fo.body_len) return -10;
   std::vector<uint8_t> hp(preimage_bound(body_off, sig.n));
   size_t pl = build_header_preimage(raw, hs, sig, hr, hp.data(), scratch);
-  if (pl != fo.pre_len || memcmp(hp.data(), pre.data(), pl) != 0) return -11;
+  if (pl != fo.pre_len || memcmp(hp.data(), pre.data(), pl) != 0) {
+    if (getenv("ZKB_EMU_DEBUG")) {
+      fprintf(stderr, "host preimage (%zu): ", pl); fwrite(hp.data(), 1, pl, stderr);
+      fprintf(stderr, "\ndevice preimage (%u): ", fo.pre_len); fwrite(pre.data(), 1, fo.pre_len, stderr); fprintf(stderr, "\n");
+    }
+    return -11;
+  }
   const Tag* tbh = sig.get("bh");
   uint8_t bh[48];
   bool bh_valid = tbh->val_len == 44 && base64_decode(sig.val(tbh), 44, bh) == 32;
@@ -236,11 +253,13 @@ int emu_fe_compare_warp(const uint8_t* raw_in, uint32_t n, const uint8_t* dom, u
   FeOut fo;
   memset(&fo, 0, sizeof fo);
   uint32_t body_l = 0;
+  static FeLut lut;
+  fe_lut_fill(&lut, 0, 1);
   emu::launch(1, 32, [&]() {
     static FeWarpSmem sm;
     FeOut mine;
     uint32_t bl = 0;
-    fe_process_warp(&sm, raw, n, dom, dom_len, k, limbs, pre.data(), sigw.data(), mine, bl, allow_skip != 0, 1);
+    fe_process_warp(&sm, &lut, raw, n, dom, dom_len, k, limbs, pre.data(), sigw.data(), mine, bl, allow_skip != 0, 1);
     if ((threadIdx.x & 31) == 0) { fo = mine; body_l = bl; }
   });
   if (scalar_rc) *scalar_rc = emu_fe_compare(raw_in, n, dom, dom_len, k, limbs, allow_skip);

@@ -57,6 +57,46 @@ def test_rsa_kernel_source(bits, limbs, lanes):
     assert sum(exp) >= 4
 
 
+def test_rsa_kernel_source_with_dedicated_squaring():
+    """rsa_verify_kernel<64, 4, false, SQR = true>: the 16 squarings of s^65537 through Mont::sqr (triangular products
+    split over the four lanes, shared-memory combine, fed reduction).  Same verdicts as the oracle, as the plain kernel,
+    and on operands built to stress the carry paths (all-ones limbs, tiny values, s = n - 1)."""
+    ks, ds, ss, exp = _rsa_cases(2048, 36)
+    assert emu.rsa_verify(ks, ds, ss, 64, 104) == exp == emu.rsa_verify(ks, ds, ss, 64, 4)
+    assert sum(exp) >= 12
+    # 1536- and 2047-bit moduli in the 64-limb class (top limbs zero), signatures that verify and near-misses
+    rng = np.random.default_rng(77)
+    for nbits in (1536, 2047, 2048):
+        while True:
+            p, q = _prime(nbits // 2, rng), _prime(nbits - nbits // 2, rng)
+            n = p * q
+            phi = (p - 1) * (q - 1)
+            if n.bit_length() == nbits and math.gcd(65537, phi) == 1:
+                break
+        d = pow(65537, -1, phi)
+        k = (nbits + 7) // 8
+        der = _der(n, 65537)
+        ks, ds, ss, exp = [], [], [], []
+        for i in range(10):
+            h = hashlib.sha256(b"sq%d" % i).digest()
+            em = b"\x00\x01" + b"\xff" * (k - 54) + b"\x00" + bytes.fromhex("3031300d060960864801650304020105000420") + h
+            s = pow(int.from_bytes(em, "big"), d, n)
+            if i == 1:
+                s ^= 1
+            elif i == 2:
+                s = n - 1
+            elif i == 3:
+                s = 1
+            elif i == 4:
+                s = (1 << (nbits - 1)) - 1      # long runs of one bits
+            elif i == 5:
+                s = 0
+            ks.append(der); ds.append(h); ss.append(s.to_bytes(k, "big"))
+            exp.append(1 if oracle.rsa_verify_sha256(der, h, ss[-1]) == 1 else 0)
+        assert exp[0] == 1 and exp[1] == 0
+        assert emu.rsa_verify(ks, ds, ss, 64, 104) == exp, nbits
+
+
 def _prime(bits, rng):
     def is_prime(n):
         if n % 2 == 0:

@@ -274,3 +274,38 @@ def test_raw_resident_batches_redo_the_front_end_every_run(engine):
                     engine.unregister_host(buf)
     finally:
         rs.close()
+
+
+def test_rsa_kernel_variant_with_dedicated_squaring():
+    """ZKB_OPT_SQR: rsa_verify_kernel<64, 4, false, SQR> (Mont::sqr for the 16 squarings of s^65537).  Same verdicts as the
+    default kernel and the oracle on forged / flipped / out-of-range signatures, and on a mixed batch end to end."""
+    from cryptography.hazmat.primitives import hashes
+    from cryptography.hazmat.primitives.asymmetric import padding
+    eng = z.Engine(flags=z.OPT_SQR, now_unix=NOW)
+    ref = z.Engine(now_unix=NOW)
+    try:
+        keys = key_pool()[2048]
+        ks, ds, ss = [], [], []
+        for i in range(300):
+            k = keys[i % len(keys)]
+            m = b"sqr%d" % i
+            sig = k.private.sign(m, padding.PKCS1v15(), hashes.SHA256())
+            d = hashlib.sha256(m).digest()
+            if i % 5 == 1:
+                sig = bytes([sig[0] ^ 1]) + sig[1:]
+            elif i % 5 == 2:
+                d = hashlib.sha256(m + b"x").digest()
+            elif i % 5 == 3:
+                sig = (b"\xff" * len(sig)) if i % 2 else (b"\x00" * (len(sig) - 1) + b"\x01")
+            ks.append(k.der); ds.append(d); ss.append(sig)
+        got = eng.rsa_verify_batch(ks, ds, ss)
+        assert got == ref.rsa_verify_batch(ks, ds, ss)
+        assert got == [1 if oracle.rsa_verify_sha256(k, d, s) == 1 else 0 for k, d, s in zip(ks, ds, ss)]
+        assert sum(got) >= 100
+        emails, labels = mixed_emails(seed=61, n_pos=40)
+        a, b = eng.verify_batch(emails), ref.verify_batch(emails)
+        assert a.tobytes() == b.tobytes()
+        for g, e, lab in zip(a, oracle.verify_batch(emails, now=NOW), labels):
+            assert_records_equal(g, e, lab)
+    finally:
+        eng.close(); ref.close()

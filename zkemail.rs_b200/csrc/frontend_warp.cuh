@@ -39,6 +39,7 @@ struct FeWarpSmem {
   uint16_t hcolon[FE_MAXH];
   uint16_t hvs[FE_MAXH];          // value start (spaces after the colon skipped)
   uint32_t hhash[FE_MAXH];        // hash of the lower-cased key
+  uint16_t hkl[FE_MAXH];          // key length for relaxed canonicalisation; bit 15: the key has a non-ASCII byte
   uint16_t seg[FE_MAXT + 2];      // tag-list segment boundaries (offsets of ';' inside the value, then its length)
   uint16_t tvoff[FE_MAXT], tvlen[FE_MAXT];
   uint8_t tcode[FE_MAXT];
@@ -49,16 +50,48 @@ struct FeWarpSmem {
   uint8_t b64[FE_B64_CAP + 8];    // base64 characters of the tag being decoded, FWS removed
 };
 
+// Character classes and base64 values, one table lookup each (shared memory on the device: lanes index it with
+// different bytes, which constant memory would serialise).
+struct FeLut { uint8_t cls[256]; uint8_t b64[256]; };
+enum { C_FWS = 1, C_VAL = 2, C_ALPHA = 4, C_ALNUM = 8, C_UPPER = 16, C_WSP = 32 };
+__device__ __forceinline__ void fe_lut_fill(FeLut* t, uint32_t tid, uint32_t nthreads) {
+  for (uint32_t c = tid; c < 256; c += nthreads) {
+    uint32_t k = 0;
+    if (fe_fws(c)) k |= C_FWS;
+    if (fe_valchar(c)) k |= C_VAL;
+    if (fe_alpha(c)) k |= C_ALPHA;
+    if (fe_alnum_(c)) k |= C_ALNUM;
+    if (c - 'A' < 26u) k |= C_UPPER;
+    if (c == ' ' || c == '\t') k |= C_WSP;
+    t->cls[c] = (uint8_t)k;
+    const int v = fe_b64(c);
+    t->b64[c] = v < 0 ? 0xFFu : (uint8_t)v;
+  }
+}
+
+// FNV-1a of a literal and its little-endian packing into words, evaluated by the compiler
+__host__ __device__ constexpr uint32_t fe_fnv(const char* s, uint32_t h = 2166136261u) { return *s ? fe_fnv(s + 1, (h ^ (uint32_t)(uint8_t)*s) * 16777619u) : h; }
+__host__ __device__ constexpr uint32_t fe_len(const char* s) { return *s ? 1u + fe_len(s + 1) : 0u; }
+__host__ __device__ constexpr uint32_t fe_word(const char* s, uint32_t k) {   // bytes 4k .. 4k+3 of the literal, zero padded
+  uint32_t w = 0, n = fe_len(s);
+  for (uint32_t b = 0; b < 4; b++) if (4 * k + b < n) w |= (uint32_t)(uint8_t)s[4 * k + b] << (8 * b);
+  return w;
+}
+
 // tag codes (bit = 1 << code in `seen`)
 enum { T_V = 0, T_A, T_B, T_BH, T_D, T_H, T_C, T_S, T_I, T_Q, T_X, T_L, T_OTHER = 31 };
 
 // The whole front end for one message, executed by one warp.  Outputs as fe_process (frontend.cuh).
-__device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint32_t n, const uint8_t* dom, uint32_t dom_len, uint32_t k,
+__device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const uint8_t* raw, uint32_t n, const uint8_t* dom, uint32_t dom_len, uint32_t k,
                                        uint32_t limbs, uint8_t* pre, uint32_t* sigw, FeOut& out, uint32_t& body_l, bool allow_skip,
                                        long long now) {
   const unsigned FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t ltm = (1u << lane) - 1u;
+  auto CLS = [&](uint32_t c) -> uint32_t { return lut->cls[c & 0xffu]; };
+  auto LOW = [&](uint32_t c) -> uint32_t { return c + ((uint32_t)(lut->cls[c & 0xffu] & C_UPPER) << 1); };
+  auto FWSQ = [&](uint32_t c) -> bool { return (lut->cls[c & 0xffu] & C_FWS) != 0; };
+  auto B64 = [&](uint32_t c) -> int { const uint32_t v = lut->b64[c & 0xffu]; return v == 0xFFu ? -1 : (int)v; };
   body_l = 0;
   out.flags = 0; out.body_off = 0; out.body_len = 0; out.pre_len = 0;
   for (int i = 0; i < 8; i++) out.bh[i] = 0;
@@ -70,7 +103,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
   const uintptr_t a0 = reinterpret_cast<uintptr_t>(raw) & ~(uintptr_t)15;
   const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(raw) - a0);
   const uint32_t want = n < FE_HB_CAP ? n : FE_HB_CAP;
-  uint32_t body_off = 0;
+  uint32_t body_off = 0, checked = 0;
   for (uint32_t base = 0; base < want + lead && !body_off; base += 512) {
     const uint32_t pos = base + lane * 16;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -83,16 +116,26 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
     }
     __syncwarp();
     const uint32_t hi = (base + 512 < want + lead ? base + 512 : want + lead) - lead;   // message bytes staged so far
-    uint32_t first = 0xffffffffu;
+    // CRLF CRLF among the candidate positions whose four bytes are staged: 16 candidates per lane out of five aligned
+    // shared-memory words (candidates that still miss bytes are looked at again in the next step)
+    {
+      const uint32_t c0 = checked + lane * 16;
+      uint32_t first = 0xffffffffu;
+      if (c0 + 4 <= hi) {
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(sm->hdr + c0);
+        uint32_t x[5];
 #pragma unroll
-    for (int q = 0; q < 16; q++) {
-      // candidates start 3 bytes before this step's first byte so that a CRLF CRLF straddling two steps is seen
-      const int32_t i = (int32_t)(pos + q) - (int32_t)lead - 3;
-      if (i >= 0 && (uint32_t)i + 4 <= hi && first == 0xffffffffu &&
-          sm->hdr[i] == '\r' && sm->hdr[i + 1] == '\n' && sm->hdr[i + 2] == '\r' && sm->hdr[i + 3] == '\n') first = (uint32_t)i;
+        for (int q = 0; q < 5; q++) x[q] = wp[q];
+#pragma unroll
+        for (int q = 15; q >= 0; q--) {
+          const uint32_t four = (q & 3) ? __funnelshift_r(x[q >> 2], x[(q >> 2) + 1], 8 * (q & 3)) : x[q >> 2];
+          if (four == 0x0a0d0a0du && c0 + q + 4 <= hi) first = c0 + q;
+        }
+      }
+      const unsigned hit = __ballot_sync(FULL, first != 0xffffffffu);
+      if (hit) body_off = __shfl_sync(FULL, first, __ffs((int)hit) - 1) + 4;
+      checked = hi >= 3 ? ((hi - 3) & ~15u) : 0u;     // every candidate below this had its four bytes
     }
-    const unsigned hit = __ballot_sync(FULL, first != 0xffffffffu);
-    if (hit) body_off = __shfl_sync(FULL, first, __ffs((int)hit) - 1) + 4;
   }
   if (!body_off) FE_FAIL(FE_FALLBACK);                  // no CRLF CRLF within FE_HB_CAP bytes
   const uint32_t hend = body_off - 2;                   // end of the last header line (its CRLF included)
@@ -102,21 +145,24 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
   // ---------------------------------------------------------------- 2. header starts; CRLF discipline
   uint32_t nh = 0;
   {
-    bool bad = false;
+    // three delimiter masks per 32 bytes; everything else is the same bit arithmetic on every lane.  Every LF must
+    // follow a CR and every CR must be followed by a LF (mailparse splits on LF alone; bare ones go to the host).
+    unsigned bad = 0, prev_lf = 1u /* a header starts at offset 0 */, prev_cr = 0u;
     for (uint32_t base = 0; base < hend; base += 32) {
       const uint32_t i = base + lane;
-      bool start = false;
-      if (i < hend) {
-        const uint32_t c = sm->hdr[i];
-        if (c == '\n') bad = bad || i == 0 || sm->hdr[i - 1] != '\r';
-        if (c == '\r') bad = bad || sm->hdr[i + 1] != '\n';          // hdr[hend] is staged (the blank line's CR)
-        start = (i == 0 || (i >= 2 && sm->hdr[i - 1] == '\n')) && c != ' ' && c != '\t';
-      }
-      const unsigned m = __ballot_sync(FULL, start);
-      if (start) { const uint32_t r = nh + __popc(m & ltm); if (r < FE_MAXH) sm->hstart[r] = (uint16_t)i; }
-      nh += __popc(m);
+      const uint32_t c = i < hend ? sm->hdr[i] : 'x';
+      const unsigned lf = __ballot_sync(FULL, c == '\n'), cr = __ballot_sync(FULL, c == '\r');
+      const unsigned ws = __ballot_sync(FULL, c == ' ' || c == '\t');
+      const unsigned valid = hend - base >= 32 ? FULL : ((1u << (hend - base)) - 1u);
+      bad |= lf & ~((cr << 1) | prev_cr);                 // LF without CR
+      bad |= (cr & 0x7fffffffu) & ~(lf >> 1);              // CR without LF (bit 31 is judged with the next step)
+      bad |= prev_cr & ~lf & 1u;
+      const unsigned starts = ((lf << 1) | prev_lf) & ~ws & valid;
+      if ((starts >> lane) & 1u) { const uint32_t r = nh + __popc(starts & ltm); if (r < FE_MAXH) sm->hstart[r] = (uint16_t)i; }
+      nh += __popc(starts);
+      prev_lf = lf >> 31; prev_cr = cr >> 31;
     }
-    if (__ballot_sync(FULL, bad)) FE_FAIL(FE_FALLBACK);
+    if (bad) FE_FAIL(FE_FALLBACK);
     if (nh > FE_MAXH) FE_FAIL(FE_FALLBACK);
     if (lane == 0) sm->hstart[nh] = (uint16_t)hend;
     __syncwarp();
@@ -127,33 +173,47 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
   unsigned sig_mask[2] = {0u, 0u};
   {
     bool bad = false;
+    constexpr uint32_t kSigHash = fe_fnv("dkim-signature");
     for (uint32_t hb = 0; hb < nh; hb += 32) {
       const uint32_t h = hb + lane;
       bool is_sig = false;
       if (h < nh) {
         const uint32_t s = sm->hstart[h], e = sm->hstart[h + 1];
-        uint32_t p = s;
-        while (p < e && sm->hdr[p] != ':' && sm->hdr[p] != '\n') p++;
+        uint32_t p = s, hv = 2166136261u, hi8 = 0;
+        for (; p < e; p++) {
+          const uint32_t c = sm->hdr[p];
+          if (c == ':' || c == '\n') break;
+          hv = (hv ^ LOW(c)) * 16777619u;
+          hi8 |= c;
+        }
         if (p >= e || sm->hdr[p] != ':') bad = true;
         else {
           sm->hcolon[h] = (uint16_t)p;
-          uint32_t hv = 2166136261u;
-          for (uint32_t t = s; t < p; t++) hv = (hv ^ fe_lower(sm->hdr[t])) * 16777619u;
           sm->hhash[h] = hv;
           uint32_t q = p + 1;
           while (q < e && sm->hdr[q] == ' ') q++;
           sm->hvs[h] = (uint16_t)q;
-          if (p - s == 14) {
-            const char* lit = "dkim-signature";
-            is_sig = true;
-            for (uint32_t j = 0; is_sig && j < 14; j++) is_sig = fe_lower(sm->hdr[s + j]) == (uint32_t)(uint8_t)lit[j];
-          }
+          uint32_t kl = p - s;                             // relaxed key: trailing SP / 0x09..0x0d dropped
+          while (kl > 0 && (sm->hdr[s + kl - 1] == ' ' || (uint32_t)(sm->hdr[s + kl - 1] - 9u) <= 4u)) kl--;
+          sm->hkl[h] = (uint16_t)(kl | ((hi8 & 0x80u) ? 0x8000u : 0u));
+          is_sig = p - s == 14 && hv == kSigHash;
         }
       }
       sig_mask[hb >> 5] = __ballot_sync(FULL, is_sig);
     }
     if (__ballot_sync(FULL, bad)) FE_FAIL(FE_FALLBACK);
     __syncwarp();
+    // the hashes matched: confirm the 14 bytes (a colliding key is just another header)
+    for (int w = 0; w < 2; w++) {
+      unsigned m = sig_mask[w];
+      while (m) {
+        const uint32_t h = 32u * (uint32_t)w + (uint32_t)__ffs((int)m) - 1u;
+        m &= m - 1;
+        const char* lit = "dkim-signature";
+        const bool eq = lane >= 14 || LOW(sm->hdr[sm->hstart[h] + lane]) == (uint32_t)(uint8_t)lit[lane];
+        if (__ballot_sync(FULL, !eq)) sig_mask[w] &= ~(1u << (h & 31u));
+      }
+    }
   }
   const uint32_t n_sigs = (uint32_t)(__popc(sig_mask[0]) + __popc(sig_mask[1]));
   if (n_sigs == 0 || n_sigs > 8) FE_FAIL(FE_FALLBACK);
@@ -165,17 +225,25 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
   // ---------------------------------------------------------------- 4. DKIM-Signature headers, top to bottom
   uint32_t so = 0, sn = 0, seen = 0;
   FeVal tv{0, 0}, ta{0, 0}, tb{0, 0}, tbh{0, 0}, td{0, 0}, th{0, 0}, tc{0, 0}, ti{0, 0}, tq{0, 0}, tx{0, 0}, tl{0, 0};
-  // compares a tag value with its FWS removed against `lit` (lane-local, short values)
-  auto val_is = [&](FeVal v, const char* lit) -> bool {
-    uint32_t j = 0;
-    for (uint32_t i = 0; i < v.len; i++) {
-      const uint32_t c = sm->hdr[so + v.off + i];
-      if (fe_fws(c)) continue;
-      if (lit[j] == 0 || (uint32_t)(uint8_t)lit[j] != c) return false;
-      j++;
-    }
-    return lit[j] == 0;
+  // A short tag value with its FWS removed, packed into four little-endian words (every lane gets the same words);
+  // len = number of characters (99 when the value cannot be one of the literals it is compared with)
+  struct Packed { uint32_t w[4]; uint32_t len; };
+  auto pack_value = [&](FeVal v) -> Packed {
+    Packed pk;
+    pk.w[0] = pk.w[1] = pk.w[2] = pk.w[3] = 0; pk.len = 99;
+    if (v.len > 32) return pk;
+    uint32_t c = 0;
+    bool keep = false;
+    if (lane < v.len) { c = sm->hdr[so + v.off + lane]; keep = !FWSQ(c); }
+    const unsigned m = __ballot_sync(FULL, keep);
+    const uint32_t r = __popc(m & ltm);
+#pragma unroll
+    for (uint32_t q = 0; q < 4; q++) pk.w[q] = __reduce_or_sync(FULL, (keep && (r >> 2) == q) ? c << (8 * (r & 3)) : 0u);
+    pk.len = __popc(m) <= 16 ? (uint32_t)__popc(m) : 99u;
+    return pk;
   };
+#define FE_IS(pk, lit) ((pk).len == fe_len(lit) && (pk).w[0] == fe_word(lit, 0) && (pk).w[1] == fe_word(lit, 1) && \
+                        (pk).w[2] == fe_word(lit, 2) && (pk).w[3] == fe_word(lit, 3))
   // 0: a well-formed rsa-sha256 signature of from_domain; 2: well-formed, another domain; 1: anything else.  Warp-uniform.
   auto parse_sig = [&](uint32_t idx) -> int {
     so = val_off(idx); sn = val_len(idx);
@@ -189,7 +257,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
         if (i < sn) {
           const uint32_t c = sm->hdr[so + i];
           semi = c == ';';
-          bad = bad || !(semi || fe_fws(c) || fe_valchar(c));       // control characters, DEL, non-ASCII
+          bad = bad || !(semi || (CLS(c) & (C_FWS | C_VAL)));       // control characters, DEL, non-ASCII
         }
         const unsigned m = __ballot_sync(FULL, semi);
         if (semi) { const uint32_t r = nseg + __popc(m & ltm); if (r < FE_MAXT) sm->seg[r] = (uint16_t)i; }
@@ -207,21 +275,21 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
     if (lane < ntag) {
       uint32_t a = lane == 0 ? 0u : (uint32_t)sm->seg[lane - 1] + 1u, b = sm->seg[lane];
       uint32_t p = a;
-      while (p < b && fe_fws(sm->hdr[so + p])) p++;
+      while (p < b && FWSQ(sm->hdr[so + p])) p++;
       if (p >= b) empty = true;
-      else if (!fe_alpha(sm->hdr[so + p])) bad = true;
+      else if (!(CLS(sm->hdr[so + p]) & C_ALPHA)) bad = true;
       else {
         const uint32_t name_off = p;
-        while (p < b && fe_alnum_(sm->hdr[so + p])) p++;
+        while (p < b && (CLS(sm->hdr[so + p]) & C_ALNUM)) p++;
         const uint32_t name_len = p - name_off;
-        while (p < b && fe_fws(sm->hdr[so + p])) p++;
+        while (p < b && FWSQ(sm->hdr[so + p])) p++;
         if (p >= b || sm->hdr[so + p] != '=') bad = true;
         else {
           p++;
-          while (p < b && fe_fws(sm->hdr[so + p])) p++;
+          while (p < b && FWSQ(sm->hdr[so + p])) p++;
           voff = p;
           uint32_t e = b;
-          while (e > p && fe_fws(sm->hdr[so + e - 1])) e--;
+          while (e > p && FWSQ(sm->hdr[so + e - 1])) e--;
           vlen = e - p;                                              // valchar runs joined by FWS (classes checked above)
           const uint32_t n0 = sm->hdr[so + name_off], n1 = name_len > 1 ? sm->hdr[so + name_off + 1] : 0u;
           if (name_len == 1) {
@@ -258,26 +326,24 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
     }
     const uint32_t need = (1u << T_V) | (1u << T_A) | (1u << T_B) | (1u << T_BH) | (1u << T_D) | (1u << T_H) | (1u << T_S);
     if ((seen & need) != need) return 1;
-    // ---- the short value checks, one per lane (same routine, different operands), then the odd ones on lane 0
+    // ---- the short literal values: packed once, compared as words
     {
-      bool ok = true;
-      if (lane == 0) ok = val_is(tv, "1");
-      else if (lane == 1) ok = val_is(ta, "rsa-sha256");
-      else if (lane == 2) ok = !(seen & (1u << T_Q)) || val_is(tq, "dns/txt");
-      if (__ballot_sync(FULL, !ok) || tb.len == 0) return 1;
+      const Packed pv = pack_value(tv), pa = pack_value(ta);
+      if (!FE_IS(pv, "1") || !FE_IS(pa, "rsa-sha256") || tb.len == 0) return 1;
+      if (seen & (1u << T_Q)) { const Packed pq = pack_value(tq); if (!FE_IS(pq, "dns/txt")) return 1; }
     }
     int rc = 0;
     uint32_t lval = 0;
     if (lane == 0) {
       if (seen & (1u << T_I)) {                                      // i= must end with the d= value (bytes, FWS removed)
         uint32_t li = 0, ld = 0;
-        for (uint32_t i = 0; i < ti.len; i++) if (!fe_fws(sm->hdr[so + ti.off + i])) li++;
-        for (uint32_t i = 0; i < td.len; i++) if (!fe_fws(sm->hdr[so + td.off + i])) ld++;
+        for (uint32_t i = 0; i < ti.len; i++) if (!FWSQ(sm->hdr[so + ti.off + i])) li++;
+        for (uint32_t i = 0; i < td.len; i++) if (!FWSQ(sm->hdr[so + td.off + i])) ld++;
         if (li < ld) rc = 1;
         uint32_t a = ti.len, b = td.len;
         for (uint32_t m = 0; m < ld && rc == 0; m++) {
-          do { a--; } while (fe_fws(sm->hdr[so + ti.off + a]));
-          do { b--; } while (fe_fws(sm->hdr[so + td.off + b]));
+          do { a--; } while (FWSQ(sm->hdr[so + ti.off + a]));
+          do { b--; } while (FWSQ(sm->hdr[so + td.off + b]));
           if (sm->hdr[so + ti.off + a] != sm->hdr[so + td.off + b]) rc = 1;
         }
       }
@@ -286,7 +352,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
         uint32_t digits = 0;
         for (uint32_t i = 0; i < tx.len && rc == 0; i++) {
           const uint32_t c = sm->hdr[so + tx.off + i];
-          if (fe_fws(c)) continue;
+          if (FWSQ(c)) continue;
           if (c < '0' || c > '9' || ++digits > 17) rc = 1;
           else x = x * 10 + (long long)(c - '0');
         }
@@ -297,7 +363,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
         unsigned long long v = 0;
         for (uint32_t i = 0; i < tl.len && rc == 0; i++) {
           const uint32_t c = sm->hdr[so + tl.off + i];
-          if (fe_fws(c)) continue;
+          if (FWSQ(c)) continue;
           if (c == '+' && digits == 0 && plus == 0) { plus = 1; continue; }
           if (c < '0' || c > '9' || ++digits > 18) rc = 1;
           else v = v * 10 + (unsigned long long)(c - '0');
@@ -305,19 +371,23 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
         if (rc == 0 && digits == 0) rc = 1;
         lval = v > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)v;
       }
-      if (rc == 0) {                                                 // d= == from_domain (ASCII case-insensitive, FWS removed)
-        uint32_t j = 0;
-        bool ok = true;
-        for (uint32_t i = 0; i < td.len && ok; i++) {
-          const uint32_t c = sm->hdr[so + td.off + i];
-          if (fe_fws(c)) continue;
-          ok = j < dom_len && fe_lower(c) == fe_lower(dom[j]);
-          j++;
-        }
-        if (!ok || j != dom_len) rc = 2;                             // a signature of another domain: the reference skips it
-      }
     }
     rc = __shfl_sync(FULL, rc, 0);
+    if (rc == 0) {                                                   // d= == from_domain (ASCII case-insensitive, FWS removed)
+      uint32_t j = 0;
+      bool differ = false;
+      for (uint32_t base = 0; base < td.len; base += 32) {
+        const uint32_t i = base + lane;
+        uint32_t c = 0;
+        bool keep = false;
+        if (i < td.len) { c = sm->hdr[so + td.off + i]; keep = !FWSQ(c); }
+        const unsigned m = __ballot_sync(FULL, keep);
+        const uint32_t r = j + __popc(m & ltm);
+        if (keep) differ = differ || r >= dom_len || LOW(c) != LOW(dom[r]);
+        j += __popc(m);
+      }
+      if (__ballot_sync(FULL, differ) || j != dom_len) rc = 2;       // a signature of another domain: the reference skips it
+    }
     body_l = __shfl_sync(FULL, lval, 0);
     return rc;
   };
@@ -336,16 +406,12 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
   const uint32_t multi = (n_sigs > 1 ? FE_MULTI : 0u) | ((seen & (1u << T_L)) ? FE_HAS_L : 0u);
   bool hr = false, br = false;
   if (seen & (1u << T_C)) {
-    // the six spellings, one per lane
-    const char* lit = lane == 0 ? "relaxed/relaxed" : lane == 1 ? "simple/simple" : lane == 2 ? "simple" : lane == 3 ? "relaxed/simple"
-                      : lane == 4 ? "relaxed" : "simple/relaxed";
-    bool m = false;
-    if (lane < 6) m = val_is(tc, lit);
-    const unsigned cm = __ballot_sync(FULL, m);
-    if (!cm) FE_FAIL(FE_FALLBACK);
-    const int w = __ffs((int)cm) - 1;
-    hr = w == 0 || w == 3 || w == 4;
-    br = w == 0 || w == 5;
+    const Packed pc = pack_value(tc);
+    if (FE_IS(pc, "relaxed/relaxed")) { hr = true; br = true; }
+    else if (FE_IS(pc, "simple/simple") || FE_IS(pc, "simple")) { hr = false; br = false; }
+    else if (FE_IS(pc, "relaxed/simple") || FE_IS(pc, "relaxed")) { hr = true; br = false; }
+    else if (FE_IS(pc, "simple/relaxed")) { hr = false; br = true; }
+    else FE_FAIL(FE_FALLBACK);
   }
 
   // ---------------------------------------------------------------- 5. h=: names, bottom-up selection
@@ -354,7 +420,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
     const uint32_t i = base + lane;
     uint32_t c = 0;
     bool keep = false;
-    if (i < th.len) { c = sm->hdr[so + th.off + i]; keep = !fe_fws(c); }
+    if (i < th.len) { c = sm->hdr[so + th.off + i]; keep = !FWSQ(c); }
     const unsigned m = __ballot_sync(FULL, keep);
     const uint32_t r = hl + __popc(m & ltm);
     if (keep && r < sizeof sm->hbuf) sm->hbuf[r] = (uint8_t)c;
@@ -388,9 +454,9 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
   if (lane < nn) {
     const uint32_t a = sm->name_s[lane], e = sm->name_e[lane];
     uint32_t hv = 2166136261u;
-    for (uint32_t t = a; t < e; t++) hv = (hv ^ fe_lower(sm->hbuf[t])) * 16777619u;
+    for (uint32_t t = a; t < e; t++) hv = (hv ^ LOW(sm->hbuf[t])) * 16777619u;
     sm->name_hash[lane] = hv;
-    has_from = e - a == 4 && fe_lower(sm->hbuf[a]) == 'f' && fe_lower(sm->hbuf[a + 1]) == 'r' && fe_lower(sm->hbuf[a + 2]) == 'o' && fe_lower(sm->hbuf[a + 3]) == 'm';
+    has_from = e - a == 4 && LOW(sm->hbuf[a]) == 'f' && LOW(sm->hbuf[a + 1]) == 'r' && LOW(sm->hbuf[a + 2]) == 'o' && LOW(sm->hbuf[a + 3]) == 'm';
   }
   if (!__ballot_sync(FULL, has_from)) FE_FAIL(FE_FALLBACK);
   __syncwarp();
@@ -405,8 +471,8 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
       const int i = 31 - __clz((int)sm_mask);
       // the hashes matched: confirm the bytes (a collision is not worth a wrong cursor)
       bool eq = true;
-      if (lane < nl) eq = fe_lower(sm->hbuf[sm->name_s[i] + lane]) == fe_lower(sm->hbuf[sm->name_s[j] + lane]);
-      for (uint32_t t = 32 + lane; t < nl; t += 32) eq = eq && fe_lower(sm->hbuf[sm->name_s[i] + t]) == fe_lower(sm->hbuf[sm->name_s[j] + t]);
+      if (lane < nl) eq = LOW(sm->hbuf[sm->name_s[i] + lane]) == LOW(sm->hbuf[sm->name_s[j] + lane]);
+      for (uint32_t t = 32 + lane; t < nl; t += 32) eq = eq && LOW(sm->hbuf[sm->name_s[i] + t]) == LOW(sm->hbuf[sm->name_s[j] + t]);
       if (__ballot_sync(FULL, !eq)) FE_FAIL(FE_FALLBACK);
       const int hprev = sm->hit_of[i];
       start = hprev >= 0 ? hprev : 0;
@@ -421,7 +487,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
     }
     if (hit >= 0) {
       bool eq = true;
-      for (uint32_t t = lane; t < nl; t += 32) eq = eq && fe_lower(sm->hdr[sm->hstart[hit] + t]) == fe_lower(sm->hbuf[sm->name_s[j] + t]);
+      for (uint32_t t = lane; t < nl; t += 32) eq = eq && LOW(sm->hdr[sm->hstart[hit] + t]) == LOW(sm->hbuf[sm->name_s[j] + t]);
       if (__ballot_sync(FULL, !eq)) FE_FAIL(FE_FALLBACK);
     }
     if (lane == 0) sm->hit_of[j] = (int16_t)hit;
@@ -439,12 +505,14 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
   auto put_raw = [&](uint32_t off, uint32_t len, bool lower) {
     for (uint32_t t = lane; t < len; t += 32) {
       const uint32_t c = sm->hdr[off + t];
-      if (o + t < FE_PRE_CAP) pre[o + t] = (uint8_t)(lower ? fe_lower(c) : c); else overflow = true;
+      if (o + t < FE_PRE_CAP) pre[o + t] = (uint8_t)(lower ? LOW(c) : c); else overflow = true;
     }
     o += len;
   };
-  // relaxed value: CR / LF dropped (they only occur as CRLF here), WSP runs collapsed to one SP, leading WSP dropped;
-  // bytes in [skip_lo, skip_hi) are absent.  State carried between calls: prev_sp.
+  // relaxed value: CR / LF dropped (they only occur as CRLF here), WSP runs collapsed to one SP, leading and trailing
+  // WSP dropped; bytes in [skip_lo, skip_hi) are absent.  A WSP byte is never written by itself: the non-WSP byte that
+  // follows a run writes the SP in front of itself, so a trailing run leaves nothing behind (no byte is written twice —
+  // lanes of a warp have no write order among each other).  State carried between calls: prev_sp, rv_start.
   bool prev_sp = true;
   uint32_t rv_start = 0;
   auto put_relaxed = [&](uint32_t off, uint32_t len, uint32_t skip_lo, uint32_t skip_hi) {
@@ -458,29 +526,29 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
         wsp = c == ' ' || c == '\t';
       }
       const unsigned pm = __ballot_sync(FULL, present), wm = __ballot_sync(FULL, present && wsp);
+      const unsigned nw = pm & ~wm;                           // bytes that are written
       const unsigned lower = pm & ltm;
       const bool prev_w = lower ? ((wm >> (31 - __clz((int)lower))) & 1u) != 0 : prev_sp;
-      const bool keep = present && (!wsp || !prev_w);
-      const unsigned km = __ballot_sync(FULL, keep);
-      if (keep) { const uint32_t at = o + __popc(km & ltm); if (at < FE_PRE_CAP) pre[at] = (uint8_t)(wsp ? ' ' : c); else overflow = true; }
-      o += __popc(km);
+      // a SP goes in front of a non-WSP byte that follows a WSP run, unless nothing of this value has been written yet
+      const bool started = o > rv_start || (nw & ltm) != 0;
+      const unsigned spm = __ballot_sync(FULL, present && !wsp && prev_w && started);
+      if ((nw >> lane) & 1u) {
+        uint32_t at = o + __popc(nw & ltm) + __popc(spm & ltm);
+        if ((spm >> lane) & 1u) { if (at < FE_PRE_CAP) pre[at] = ' '; else overflow = true; at++; }
+        if (at < FE_PRE_CAP) pre[at] = (uint8_t)c; else overflow = true;
+      }
+      o += __popc(nw) + __popc(spm);
       if (pm) prev_sp = ((wm >> (31 - __clz((int)pm))) & 1u) != 0;
     }
   };
-  auto finish_relaxed = [&]() {
-    if (prev_sp && o > rv_start) o--;          // the value ended in a WSP run that was emitted as one SP
-    put_lit("\r\n", 2);
-  };
+  auto finish_relaxed = [&]() { put_lit("\r\n", 2); };
   for (uint32_t j = 0; j < nn; j++) {
     const int hit = sm->hit_of[j];
     if (hit < 0) continue;
     const uint32_t ks = sm->hstart[hit], kl0 = (uint32_t)sm->hcolon[hit] - ks;
-    bool hi8 = false;
-    for (uint32_t t = lane; t < kl0; t += 32) hi8 = hi8 || (sm->hdr[ks + t] & 0x80) != 0;
-    if (__ballot_sync(FULL, hi8)) FE_FAIL(FE_FALLBACK);
+    if (sm->hkl[hit] & 0x8000u) FE_FAIL(FE_FALLBACK);            // non-ASCII byte in a selected key
     if (hr) {
-      uint32_t kl = kl0;
-      while (kl > 0 && (sm->hdr[ks + kl - 1] == ' ' || (sm->hdr[ks + kl - 1] >= 9 && sm->hdr[ks + kl - 1] <= 13))) kl--;
+      const uint32_t kl = sm->hkl[hit] & 0x7fffu;
       put_raw(ks, kl, true);
       put_lit(":", 1);
       prev_sp = true; rv_start = o;
@@ -529,7 +597,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
       const uint32_t i = base + lane;
       uint32_t c = 0;
       bool keep = false;
-      if (i < v.len) { c = sm->hdr[so + v.off + i]; keep = !fe_fws(c); }
+      if (i < v.len) { c = sm->hdr[so + v.off + i]; keep = !FWSQ(c); }
       const unsigned m = __ballot_sync(FULL, keep);
       const uint32_t r = cnt + __popc(m & ltm);
       if (keep && r < FE_B64_CAP) sm->b64[r] = (uint8_t)c;
@@ -548,7 +616,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
       const uint32_t q = qb + lane;
       if (q < nq) {
         const uint32_t c0 = sm->b64[4 * q], c1 = sm->b64[4 * q + 1], c2 = sm->b64[4 * q + 2], c3 = sm->b64[4 * q + 3];
-        const int a = fe_b64(c0), b = fe_b64(c1), c = fe_b64(c2), d = fe_b64(c3);
+        const int a = B64(c0), b = B64(c1), c = B64(c2), d = B64(c3);
         if (a < 0 || b < 0) bad = true;
         else if (!(c >= 0 && d >= 0)) {
           if (q + 1 != nq) bad = true;
@@ -566,7 +634,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
   // decoded byte i (from the start) out of sm->b64
   auto byte_at = [&](uint32_t i) -> uint32_t {
     const uint32_t q = i / 3, r = i - 3 * q;
-    const uint32_t a = (uint32_t)fe_b64(sm->b64[4 * q + r]) & 63u, b = (uint32_t)fe_b64(sm->b64[4 * q + r + 1]) & 63u;
+    const uint32_t a = (uint32_t)lut->b64[sm->b64[4 * q + r]] & 63u, b = (uint32_t)lut->b64[sm->b64[4 * q + r + 1]] & 63u;
     return r == 0 ? ((a << 2) | (b >> 4)) & 0xffu : r == 1 ? ((a << 4) | (b >> 2)) & 0xffu : ((a << 6) | b) & 0xffu;
   };
   {
@@ -602,12 +670,13 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const uint8_t* raw, uint3
   }
   out.flags = flags;
 #undef FE_FAIL
+#undef FE_IS
 }
 
 #ifdef ZKB_HOST_EMU
-#define ZKB_FE_SMEM(name) static FeWarpSmem name[FE_WARPS]
+#define ZKB_FE_SMEM(name) static FeWarpSmem name[FE_WARPS]; static FeLut name##_lut
 #else
-#define ZKB_FE_SMEM(name) __shared__ FeWarpSmem name[FE_WARPS]
+#define ZKB_FE_SMEM(name) __shared__ FeWarpSmem name[FE_WARPS]; __shared__ FeLut name##_lut
 #endif
 
 // One warp per message.  Also emits the body's CanonItem (an empty one for fallback / error messages).
@@ -617,13 +686,15 @@ frontend_warp_kernel(const uint8_t* __restrict__ span, const FeIn* __restrict__ 
                      uint32_t* __restrict__ cand_bh, CanonItem* __restrict__ canon, FeOut* __restrict__ out, int allow_skip,
                      long long now) {
   ZKB_FE_SMEM(smem);
+  fe_lut_fill(&smem_lut, threadIdx.x, FE_WARPS * 32);
+  __syncthreads();
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t idx = blockIdx.x * FE_WARPS + warp;
   if (idx >= n) return;
   const FeIn fi = in[idx];
   FeOut fo;
   uint32_t body_l = 0;
-  fe_process_warp(&smem[warp], span + fi.raw_off, fi.raw_len, arena + fi.dom_off, fi.dom_len, fi.k, fi.limbs, arena + msg_off[fi.pre_msg],
+  fe_process_warp(&smem[warp], &smem_lut, span + fi.raw_off, fi.raw_len, arena + fi.dom_off, fi.dom_len, fi.k, fi.limbs, arena + msg_off[fi.pre_msg],
                   sig_arena + fi.sig_word_off, fo, body_l, allow_skip != 0, now);
   if (lane != 0) return;
   const bool live = (fo.flags & (FE_FALLBACK | FE_MAIL_PARSE)) == 0;

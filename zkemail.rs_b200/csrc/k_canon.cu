@@ -6,7 +6,8 @@ void launch_canon_body(const uint8_t* span, const CanonItem* items, uint32_t n, 
   if (!n) return;
   // lane = message: chunks of the e2e pipeline hold ~64 K messages, which 128-thread CTAs spread unevenly (3 or 4
   // CTAs per SM); small CTAs balance them (an SM holds 32 CTAs, so only while that does not cap the occupancy)
-  const unsigned block = n <= 148u * 1024u ? 32u : n <= 148u * 2048u ? 64u : 128u;
-  canon_body_kernel<<<(n + block - 1) / block, block, 0, s>>>(span, items, n, arena, msg_off, msg_len);
+  // staged form: lane = body, bytes move through shared memory in coalesced 128-byte segments (canon.cuh)
+  const unsigned per_cta = CANON_WARPS * 32;
+  canon_body_staged_kernel<<<(n + per_cta - 1) / per_cta, per_cta, 0, s>>>(span, items, n, arena, msg_off, msg_len);
 }
 }  // namespace zkb

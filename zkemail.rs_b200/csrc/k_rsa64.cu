@@ -15,8 +15,15 @@ static void launch_t(int lanes, const uint32_t* sig_arena, const RsaItem* items,
 #undef ZKB_RSA_CASE
 }
 void launch_rsa64(bool generic, int lanes, const uint32_t* sig_arena, const RsaItem* items, uint32_t n,
-                  const uint32_t* keytab, const uint32_t* digests, uint32_t* cand_flags, cudaStream_t s) {
+                  const uint32_t* keytab, const uint32_t* digests, uint32_t* cand_flags, cudaStream_t s, bool sqr) {
   if (!n) return;
+  if (sqr && !generic && lanes == 4) {
+    // e = 65537, four lanes per signature: the variant with the dedicated squaring (Mont::sqr), 64-thread CTAs
+    const unsigned block = 64;
+    const unsigned grid = (unsigned)(((uint64_t)n * 4 + block - 1) / block);
+    rsa_verify_kernel<64, 4, false, true><<<grid, block, 0, s>>>(sig_arena, items, n, keytab, digests, cand_flags);
+    return;
+  }
   if (generic) launch_t<true>(lanes, sig_arena, items, n, keytab, digests, cand_flags, s);
   else launch_t<false>(lanes, sig_arena, items, n, keytab, digests, cand_flags, s);
 }

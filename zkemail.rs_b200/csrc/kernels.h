@@ -17,8 +17,9 @@ void launch_rsa(int limbs, bool generic, int lanes, const uint32_t* sig_arena, c
                 const uint32_t* keytab, const uint32_t* digests, uint32_t* cand_flags, cudaStream_t s);
 void launch_rsa32(bool generic, int lanes, const uint32_t* sig_arena, const RsaItem* items, uint32_t n,
                   const uint32_t* keytab, const uint32_t* digests, uint32_t* cand_flags, cudaStream_t s);
+// sqr: four lanes per signature and e = 65537 use the kernel variant with the dedicated Montgomery squaring
 void launch_rsa64(bool generic, int lanes, const uint32_t* sig_arena, const RsaItem* items, uint32_t n,
-                  const uint32_t* keytab, const uint32_t* digests, uint32_t* cand_flags, cudaStream_t s);
+                  const uint32_t* keytab, const uint32_t* digests, uint32_t* cand_flags, cudaStream_t s, bool sqr = false);
 void launch_rsa128(bool generic, int lanes, const uint32_t* sig_arena, const RsaItem* items, uint32_t n,
                    const uint32_t* keytab, const uint32_t* digests, uint32_t* cand_flags, cudaStream_t s);
 cudaError_t dfa_set_smem_limit(size_t bytes);
