@@ -144,7 +144,7 @@ void emu_canon_body(const uint8_t* span, const uint64_t* off, const uint32_t* le
   }
   const unsigned block = 128;
   if (getenv("ZKB_EMU_CANON_UNSTAGED")) emu::launch((n + block - 1) / block, block, [&]() { canon_body_kernel(span, items.data(), n, arena, slot_off, out_len); });
-  else emu::launch((n + block - 1) / block, block, [&]() { canon_body_staged_kernel(span, items.data(), n, arena, slot_off, out_len); });
+  else emu::launch((n + block - 1) / block, block, [&]() { canon_body_staged_kernel(span, items.data(), n, arena, slot_off, out_len, nullptr, nullptr, n); });
 }
 
 // What the device front end produced for one message, checked against the host front end (dkim_host.hpp).

@@ -197,18 +197,23 @@ struct CanonOutS {             // CanonOut writing into the lane's shared-memory
 
 __global__ void __launch_bounds__(CANON_WARPS * 32)
 canon_body_staged_kernel(const uint8_t* __restrict__ span, const CanonItem* __restrict__ items, uint32_t n_items,
-                         uint8_t* __restrict__ arena, const uint64_t* __restrict__ msg_off, uint32_t* __restrict__ msg_len) {
+                         uint8_t* __restrict__ arena, const uint64_t* __restrict__ msg_off, uint32_t* __restrict__ msg_len,
+                         const uint32_t* __restrict__ order, const uint32_t* __restrict__ msg_canon, uint32_t n_lanes) {
   ZKB_CANON_SMEM(smem);
   const unsigned FULL = 0xffffffffu;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* in_rows = smem + warp * 32 * (CANON_IN_PITCH + CANON_OUT_PITCH);
   uint8_t* out_rows = in_rows + 32 * CANON_IN_PITCH;
   const uint32_t idx = (blockIdx.x * CANON_WARPS + warp) * 32 + lane;
-  if ((blockIdx.x * CANON_WARPS + warp) * 32 >= n_items) return;   // whole warp out of range
+  if ((blockIdx.x * CANON_WARPS + warp) * 32 >= n_lanes) return;   // whole warp out of range
   CanonItem it;
   it.raw_off = 0; it.raw_len = 0; it.msg = 0; it.flags = 0; it.l = 0;
-  const bool live = idx < n_items;
-  if (live) it = items[idx];
+  // lane -> item: in index order, or (order + msg_canon given) the idx-th message of the SHA order when it is a body
+  uint32_t item = idx < n_lanes ? idx : 0xFFFFFFFFu;
+  if (order && msg_canon && idx < n_lanes) item = msg_canon[order[idx]];
+  const bool live = item < n_items;
+  if (__ballot_sync(0xffffffffu, live) == 0) return;               // a warp without bodies (headers, domains, keys)
+  if (live) it = items[item];
   const uint8_t* in = span + it.raw_off;
   const uint32_t n = live ? it.raw_len : 0u;
   const bool relaxed = (it.flags & 1u) != 0;

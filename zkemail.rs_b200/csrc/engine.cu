@@ -277,6 +277,7 @@ struct DeviceChunk {   // everything one chunk needs in HBM
   DevBuf arena, meta, out, span;   // span: raw message bytes DMA'd from registered host memory (direct mode)
   const uint8_t* raw_base = nullptr;   // what raw offsets are relative to: span (direct mode) or the arena (staged raw messages)
   const CanonItem* canon_items = nullptr; uint32_t n_canon = 0;
+  const uint32_t* msg_canon = nullptr;   // message index -> canon item (or ~0): bodies are canonicalised in the SHA order (similar lengths per warp)
   uint32_t* msg_len_rw = nullptr;
   const FeIn* fe_in = nullptr; FeOut* fe_out = nullptr; uint32_t n_fe = 0;   // device front end
   CanonItem* canon_rw = nullptr; uint32_t* cand_bh_rw = nullptr; uint32_t* sig_rw = nullptr;
@@ -307,7 +308,7 @@ struct Chunk {  // host view of one chunk
   // direct mode: raw bodies stay in the caller's registered memory and are canonicalised on the device
   bool direct = false;
   const uint8_t* span_host = nullptr;
-  size_t span_bytes = 0, o_canon = 0;
+  size_t span_bytes = 0, o_canon = 0, o_msg_canon = 0;
   uint32_t n_canon = 0;
   // device front end (frontend.cuh): headers parsed / preimages built / base64 decoded on the device too
   bool fe = false;
@@ -867,6 +868,7 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
   ch.o_msg_off = o; o += align_up((size_t)M * 8, 16);
   ch.o_msg_len = o; o += align_up((size_t)M * 4, 16);
   ch.o_order = o; o += align_up((size_t)M * 4, 16);
+  ch.o_msg_canon = o; o += align_up((size_t)M * 4, 16);
   ch.o_cand_body = o; o += align_up((size_t)C * 4, 16);
   for (int k = 0; k < 6; k++) { ch.o_rsa[k] = o; ch.rsa_n[k] = rn[k]; o += align_up((size_t)rn[k] * sizeof(RsaItem), 16); }
   ch.o_dfa = o; o += align_up((size_t)n_dfa * 2 * sizeof(DfaItem), 16);  // header haystack + body haystack per email
@@ -901,11 +903,14 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
       const uint32_t nb = (m.len >> 6) + 1 + ((m.len & 63) >= 56 ? 1u : 0u);
       order[os[nb]++] = t.msg_base + (uint32_t)i;
     }
+    uint32_t* msg_canon = (uint32_t*)(mh + ch.o_msg_canon);
+    for (size_t i = 0; i < t.msgs.size(); i++) msg_canon[t.msg_base + i] = 0xFFFFFFFFu;
     uint32_t fill[6];
     for (int k = 0; k < 6; k++) fill[k] = rsa_start[(size_t)tid * 6 + k];
     for (size_t i = 0; i < t.cands.size(); i++) {
       const CandRec& cd = t.cands[i];
       cand_body[t.cand_base + i] = t.msg_base + cd.body_msg;
+      if (ch.fe) msg_canon[t.msg_base + cd.body_msg] = t.cand_base + (uint32_t)i;   // the front end writes canon item [candidate]
       if (!ch.fe) memcpy(cand_bh + (size_t)(t.cand_base + i) * 8, cd.bh, 32);
       if (cd.haystack_only || cd.sig_state != SIG_OK || cd.algo != 1) continue;
       RsaItem it;
@@ -917,7 +922,7 @@ int pack_chunk(zkb_engine* e, const zkb_email_view* emails, size_t e0, size_t ne
     }
     if (!t.sigw.empty()) memcpy(sigw + sig_base[tid], t.sigw.data(), t.sigw.size() * 4);
     CanonItem* ci = (CanonItem*)(mh + ch.o_canon) + t.canon_base;
-    for (size_t i = 0; i < t.canon.size(); i++) { ci[i] = t.canon[i]; ci[i].msg += t.msg_base; }
+    for (size_t i = 0; i < t.canon.size(); i++) { ci[i] = t.canon[i]; ci[i].msg += t.msg_base; msg_canon[ci[i].msg] = t.canon_base + (uint32_t)i; }
     if (ch.fe) {
       FeIn* fin = (FeIn*)(mh + ch.o_fein);
       for (size_t j = 0; j < t.fe_emails.size(); j++) {
@@ -1060,6 +1065,7 @@ int upload_chunk(zkb_engine* e, Chunk& ch, const zkb_regex_set* rs, DeviceChunk&
   if (d.raw_base && ch.n_canon) {
     d.canon_items = (const CanonItem*)(d.meta.p + ch.o_canon);
     d.n_canon = ch.n_canon;
+    d.msg_canon = (const uint32_t*)(d.meta.p + ch.o_msg_canon);
   }
   d.msg_len_rw = (uint32_t*)(d.meta.p + ch.o_msg_len);
   if (ch.fe && ch.C) {
@@ -1138,7 +1144,7 @@ int launch_chunk(zkb_engine* e, const DeviceChunk& d, const zkb_regex_set* rs, c
                     (long long)(e->now_unix ? e->now_unix : (int64_t)time(nullptr)), s);
     nl++;
   }
-  if (pre && d.n_canon) { launch_canon_body(d.raw_base, d.canon_items, d.n_canon, d.arena.p, d.msg_off, d.msg_len_rw, s); nl++; }
+  if (pre && d.n_canon) { launch_canon_body(d.raw_base, d.canon_items, d.n_canon, d.arena.p, d.msg_off, d.msg_len_rw, d.order, d.msg_canon, d.M, s); nl++; }
   if (ev) CK(cudaEventRecord(ev[0], s));
   if (pre && d.M) { launch_sha256(d.arena.p, d.msg_off, d.msg_len, d.order, d.M, d.digests, s); nl++; }
   if (ev) CK(cudaEventRecord(ev[1], s));
@@ -1908,7 +1914,7 @@ static int batch_prepare_impl(zkb_engine* e, const zkb_email_view* emails, size_
     if (d->n_canon) {
       // resident form: device-side canonicalisation is part of getting the batch resident (it is what
       // the host threads do on the pageable path); zkb_batch_run then launches the verification kernels
-      launch_canon_body(d->span.p, d->canon_items, d->n_canon, d->arena.p, d->msg_off, d->msg_len_rw, s);
+      launch_canon_body(d->span.p, d->canon_items, d->n_canon, d->arena.p, d->msg_off, d->msg_len_rw, d->order, d->msg_canon, d->M, s);
       d->n_canon = 0;
     }
     if (cudaStreamSynchronize(s) != cudaSuccess) { rc = ZKB_E_CUDA; break; }

@@ -29,8 +29,10 @@ void launch_dfa(uint32_t elem, bool direct, const uint8_t* arena, const DfaItem*
 void launch_dfa_strided(uint32_t elem, bool direct, const uint8_t* arena, const DfaItem* items, uint32_t n_emails, const uint32_t* msg_len, uint32_t which,
                         uint32_t P, uint32_t pi, const uint8_t* fwd_blob, uint32_t fwd_bytes, const uint8_t* rev_blob,
                         uint32_t rev_bytes, size_t smem_limit, int qp, uint4* out, cudaStream_t s);
+// order / msg_canon (optional): walk the messages in the SHA order (descending length) and canonicalise those that are
+// bodies, so that the 32 bodies of a warp have similar lengths; without them items are taken in index order
 void launch_canon_body(const uint8_t* span, const CanonItem* items, uint32_t n, uint8_t* arena, const uint64_t* msg_off,
-                       uint32_t* msg_len, cudaStream_t s);
+                       uint32_t* msg_len, const uint32_t* order, const uint32_t* msg_canon, uint32_t n_msgs, cudaStream_t s);
 void launch_frontend(const uint8_t* span, const FeIn* in, uint32_t n, uint8_t* arena, const uint64_t* msg_off, uint32_t* msg_len,
                      uint32_t* sig_arena, uint32_t* cand_bh, CanonItem* canon, FeOut* out, bool allow_skip, long long now, cudaStream_t s);
 // per-email result records (assemble.cuh); rec_words = record stride in 32-bit words
