@@ -16,3 +16,4 @@ from .generator import (  # noqa: F401,E402
 )
 from .file import from_serde, read_email_file, read_json_file, to_serde, write_json_file  # noqa: F401,E402
 from .multi import Comm, MultiBatch, MultiEngine, MultiRegexSet, plan_shards, records_to_results  # noqa: F401,E402
+from .borsh_io import BorshError, from_borsh, to_borsh  # noqa: F401,E402
