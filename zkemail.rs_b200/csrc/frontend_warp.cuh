@@ -48,6 +48,7 @@ struct FeWarpSmem {
   uint32_t name_hash[FE_MAXN];
   int16_t hit_of[FE_MAXN];
   uint8_t b64[FE_B64_CAP + 8];    // base64 characters of the tag being decoded, FWS removed
+  uint8_t dec[FE_B64_CAP / 4 * 3 + 8];   // their decoded bytes (written by the validation pass, one quad per lane)
 };
 
 // Character classes and base64 values, one table lookup each (shared memory on the device: lanes index it with
@@ -577,7 +578,9 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
   if (hr) {
     put_lit("dkim-signature:", 15);
     prev_sp = true; rv_start = o;
-    put_relaxed(so, sn, tb.off, tb.off + tb.len);
+    // the b= value (most of the header) is absent: only the bytes before and after it are walked, with the state carried
+    put_relaxed(so, tb.off, 0xffffffffu, 0xffffffffu);
+    put_relaxed(so + tb.off + tb.len, sn - tb.off - tb.len, 0xffffffffu, 0xffffffffu);
     finish_relaxed();
   } else {
     put_lit("DKIM-Signature: ", 16);
@@ -617,6 +620,11 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
       if (q < nq) {
         const uint32_t c0 = sm->b64[4 * q], c1 = sm->b64[4 * q + 1], c2 = sm->b64[4 * q + 2], c3 = sm->b64[4 * q + 3];
         const int a = B64(c0), b = B64(c1), c = B64(c2), d = B64(c3);
+        // the decoded bytes go to sm->dec as the quad is judged (bytes of a padded or broken quad are never read)
+        const uint32_t ua = (uint32_t)a & 63u, ub = (uint32_t)b & 63u, uc = (uint32_t)c & 63u, ud = (uint32_t)d & 63u;
+        sm->dec[3 * q] = (uint8_t)((ua << 2) | (ub >> 4));
+        sm->dec[3 * q + 1] = (uint8_t)((ub << 4) | (uc >> 2));
+        sm->dec[3 * q + 2] = (uint8_t)((uc << 6) | ud);
         if (a < 0 || b < 0) bad = true;
         else if (!(c >= 0 && d >= 0)) {
           if (q + 1 != nq) bad = true;
@@ -626,17 +634,13 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
         }
       }
     }
+    __syncwarp();
     if (__ballot_sync(FULL, bad)) return -1;
     const unsigned pm = __ballot_sync(FULL, pad != 0);
     const uint32_t p = pm ? __shfl_sync(FULL, pad, __ffs((int)pm) - 1) : 0u;
     return (int)(3 * nq - p);
   };
-  // decoded byte i (from the start) out of sm->b64
-  auto byte_at = [&](uint32_t i) -> uint32_t {
-    const uint32_t q = i / 3, r = i - 3 * q;
-    const uint32_t a = (uint32_t)lut->b64[sm->b64[4 * q + r]] & 63u, b = (uint32_t)lut->b64[sm->b64[4 * q + r + 1]] & 63u;
-    return r == 0 ? ((a << 2) | (b >> 4)) & 0xffu : r == 1 ? ((a << 4) | (b >> 2)) & 0xffu : ((a << 6) | b) & 0xffu;
-  };
+  auto byte_at = [&](uint32_t i) -> uint32_t { return sm->dec[i]; };   // decoded byte i (from the start)
   {
     const uint32_t cnt = compact(tbh);
     int dl = -1;
