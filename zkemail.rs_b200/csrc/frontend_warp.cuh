@@ -33,8 +33,8 @@ namespace zkb {
 #define FE_B64_CAP 704     // base64 characters of b= (4096-bit signature: 684)
 #define FE_WARPS 4         // warps (messages) per CTA
 
-struct FeWarpSmem {
-  uint8_t hdr[FE_HB_CAP + 48];
+struct __align__(16) FeWarpSmem {
+  uint8_t hdr_raw[FE_HB_CAP + 80];   // the staged bytes in the 16-byte phase of global memory: message byte i = hdr_raw[lead + i]
   uint16_t hstart[FE_MAXH + 2];   // header starts, then the end of the header block (offset of the blank line)
   uint16_t hcolon[FE_MAXH];
   uint16_t hvs[FE_MAXH];          // value start (spaces after the colon skipped)
@@ -105,42 +105,39 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
   const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(raw) - a0);
   const uint32_t want = n < FE_HB_CAP ? n : FE_HB_CAP;
   uint32_t body_off = 0, checked = 0;
+  const uint8_t* hdr = sm->hdr_raw + lead;              // message byte i
   for (uint32_t base = 0; base < want + lead && !body_off; base += 512) {
+    // every lane one aligned 16-byte block, stored as it is (the shared-memory copy keeps the phase of global memory)
     const uint32_t pos = base + lane * 16;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (pos < want + lead) v = __ldg(reinterpret_cast<const uint4*>(a0 + pos));
-    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int q = 0; q < 16; q++) {
-      const int32_t i = (int32_t)(pos + q) - (int32_t)lead;
-      if (i >= 0 && (uint32_t)i < want) sm->hdr[i] = (uint8_t)(w4[q >> 2] >> ((q & 3) * 8));
-    }
+    *reinterpret_cast<uint4*>(sm->hdr_raw + pos) = v;
     __syncwarp();
-    const uint32_t hi = (base + 512 < want + lead ? base + 512 : want + lead) - lead;   // message bytes staged so far
-    // CRLF CRLF among the candidate positions whose four bytes are staged: 16 candidates per lane out of five aligned
-    // shared-memory words (candidates that still miss bytes are looked at again in the next step)
+    const uint32_t hi = (base + 512 < want + lead ? base + 512 : want + lead);   // raw bytes staged so far (incl. the lead)
+    // CRLF CRLF among the candidate positions (raw coordinates) whose four bytes are staged: 16 candidates per lane out
+    // of five aligned shared-memory words; candidates that still miss bytes are looked at again in the next step
     {
       const uint32_t c0 = checked + lane * 16;
       uint32_t first = 0xffffffffu;
       if (c0 + 4 <= hi) {
-        const uint32_t* wp = reinterpret_cast<const uint32_t*>(sm->hdr + c0);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(sm->hdr_raw + c0);
         uint32_t x[5];
 #pragma unroll
         for (int q = 0; q < 5; q++) x[q] = wp[q];
 #pragma unroll
         for (int q = 15; q >= 0; q--) {
           const uint32_t four = (q & 3) ? __funnelshift_r(x[q >> 2], x[(q >> 2) + 1], 8 * (q & 3)) : x[q >> 2];
-          if (four == 0x0a0d0a0du && c0 + q + 4 <= hi) first = c0 + q;
+          if (four == 0x0a0d0a0du && c0 + q >= lead && c0 + q + 4 <= hi) first = c0 + q;
         }
       }
       const unsigned hit = __ballot_sync(FULL, first != 0xffffffffu);
-      if (hit) body_off = __shfl_sync(FULL, first, __ffs((int)hit) - 1) + 4;
+      if (hit) body_off = __shfl_sync(FULL, first, __ffs((int)hit) - 1) + 4 - lead;
       checked = hi >= 3 ? ((hi - 3) & ~15u) : 0u;     // every candidate below this had its four bytes
     }
   }
   if (!body_off) FE_FAIL(FE_FALLBACK);                  // no CRLF CRLF within FE_HB_CAP bytes
   const uint32_t hend = body_off - 2;                   // end of the last header line (its CRLF included)
-  const uint32_t c0 = sm->hdr[0];
+  const uint32_t c0 = hdr[0];
   if (c0 == '\r' || c0 == '\n' || c0 == ' ' || c0 == '\t') FE_FAIL(FE_FALLBACK);   // empty / malformed first line: host decides
 
   // ---------------------------------------------------------------- 2. header starts; CRLF discipline
@@ -151,7 +148,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
     unsigned bad = 0, prev_lf = 1u /* a header starts at offset 0 */, prev_cr = 0u;
     for (uint32_t base = 0; base < hend; base += 32) {
       const uint32_t i = base + lane;
-      const uint32_t c = i < hend ? sm->hdr[i] : 'x';
+      const uint32_t c = i < hend ? hdr[i] : 'x';
       const unsigned lf = __ballot_sync(FULL, c == '\n'), cr = __ballot_sync(FULL, c == '\r');
       const unsigned ws = __ballot_sync(FULL, c == ' ' || c == '\t');
       const unsigned valid = hend - base >= 32 ? FULL : ((1u << (hend - base)) - 1u);
@@ -182,20 +179,20 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
         const uint32_t s = sm->hstart[h], e = sm->hstart[h + 1];
         uint32_t p = s, hv = 2166136261u, hi8 = 0;
         for (; p < e; p++) {
-          const uint32_t c = sm->hdr[p];
+          const uint32_t c = hdr[p];
           if (c == ':' || c == '\n') break;
           hv = (hv ^ LOW(c)) * 16777619u;
           hi8 |= c;
         }
-        if (p >= e || sm->hdr[p] != ':') bad = true;
+        if (p >= e || hdr[p] != ':') bad = true;
         else {
           sm->hcolon[h] = (uint16_t)p;
           sm->hhash[h] = hv;
           uint32_t q = p + 1;
-          while (q < e && sm->hdr[q] == ' ') q++;
+          while (q < e && hdr[q] == ' ') q++;
           sm->hvs[h] = (uint16_t)q;
           uint32_t kl = p - s;                             // relaxed key: trailing SP / 0x09..0x0d dropped
-          while (kl > 0 && (sm->hdr[s + kl - 1] == ' ' || (uint32_t)(sm->hdr[s + kl - 1] - 9u) <= 4u)) kl--;
+          while (kl > 0 && (hdr[s + kl - 1] == ' ' || (uint32_t)(hdr[s + kl - 1] - 9u) <= 4u)) kl--;
           sm->hkl[h] = (uint16_t)(kl | ((hi8 & 0x80u) ? 0x8000u : 0u));
           is_sig = p - s == 14 && hv == kSigHash;
         }
@@ -211,7 +208,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
         const uint32_t h = 32u * (uint32_t)w + (uint32_t)__ffs((int)m) - 1u;
         m &= m - 1;
         const char* lit = "dkim-signature";
-        const bool eq = lane >= 14 || LOW(sm->hdr[sm->hstart[h] + lane]) == (uint32_t)(uint8_t)lit[lane];
+        const bool eq = lane >= 14 || LOW(hdr[sm->hstart[h] + lane]) == (uint32_t)(uint8_t)lit[lane];
         if (__ballot_sync(FULL, !eq)) sig_mask[w] &= ~(1u << (h & 31u));
       }
     }
@@ -235,7 +232,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
     if (v.len > 32) return pk;
     uint32_t c = 0;
     bool keep = false;
-    if (lane < v.len) { c = sm->hdr[so + v.off + lane]; keep = !FWSQ(c); }
+    if (lane < v.len) { c = hdr[so + v.off + lane]; keep = !FWSQ(c); }
     const unsigned m = __ballot_sync(FULL, keep);
     const uint32_t r = __popc(m & ltm);
 #pragma unroll
@@ -256,7 +253,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
         const uint32_t i = base + lane;
         bool semi = false;
         if (i < sn) {
-          const uint32_t c = sm->hdr[so + i];
+          const uint32_t c = hdr[so + i];
           semi = c == ';';
           bad = bad || !(semi || (CLS(c) & (C_FWS | C_VAL)));       // control characters, DEL, non-ASCII
         }
@@ -276,23 +273,23 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
     if (lane < ntag) {
       uint32_t a = lane == 0 ? 0u : (uint32_t)sm->seg[lane - 1] + 1u, b = sm->seg[lane];
       uint32_t p = a;
-      while (p < b && FWSQ(sm->hdr[so + p])) p++;
+      while (p < b && FWSQ(hdr[so + p])) p++;
       if (p >= b) empty = true;
-      else if (!(CLS(sm->hdr[so + p]) & C_ALPHA)) bad = true;
+      else if (!(CLS(hdr[so + p]) & C_ALPHA)) bad = true;
       else {
         const uint32_t name_off = p;
-        while (p < b && (CLS(sm->hdr[so + p]) & C_ALNUM)) p++;
+        while (p < b && (CLS(hdr[so + p]) & C_ALNUM)) p++;
         const uint32_t name_len = p - name_off;
-        while (p < b && FWSQ(sm->hdr[so + p])) p++;
-        if (p >= b || sm->hdr[so + p] != '=') bad = true;
+        while (p < b && FWSQ(hdr[so + p])) p++;
+        if (p >= b || hdr[so + p] != '=') bad = true;
         else {
           p++;
-          while (p < b && FWSQ(sm->hdr[so + p])) p++;
+          while (p < b && FWSQ(hdr[so + p])) p++;
           voff = p;
           uint32_t e = b;
-          while (e > p && FWSQ(sm->hdr[so + e - 1])) e--;
+          while (e > p && FWSQ(hdr[so + e - 1])) e--;
           vlen = e - p;                                              // valchar runs joined by FWS (classes checked above)
-          const uint32_t n0 = sm->hdr[so + name_off], n1 = name_len > 1 ? sm->hdr[so + name_off + 1] : 0u;
+          const uint32_t n0 = hdr[so + name_off], n1 = name_len > 1 ? hdr[so + name_off + 1] : 0u;
           if (name_len == 1) {
             switch (n0) {
               case 'v': code = T_V; break; case 'a': code = T_A; break; case 'b': code = T_B; break; case 'd': code = T_D; break;
@@ -338,21 +335,21 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
     if (lane == 0) {
       if (seen & (1u << T_I)) {                                      // i= must end with the d= value (bytes, FWS removed)
         uint32_t li = 0, ld = 0;
-        for (uint32_t i = 0; i < ti.len; i++) if (!FWSQ(sm->hdr[so + ti.off + i])) li++;
-        for (uint32_t i = 0; i < td.len; i++) if (!FWSQ(sm->hdr[so + td.off + i])) ld++;
+        for (uint32_t i = 0; i < ti.len; i++) if (!FWSQ(hdr[so + ti.off + i])) li++;
+        for (uint32_t i = 0; i < td.len; i++) if (!FWSQ(hdr[so + td.off + i])) ld++;
         if (li < ld) rc = 1;
         uint32_t a = ti.len, b = td.len;
         for (uint32_t m = 0; m < ld && rc == 0; m++) {
-          do { a--; } while (FWSQ(sm->hdr[so + ti.off + a]));
-          do { b--; } while (FWSQ(sm->hdr[so + td.off + b]));
-          if (sm->hdr[so + ti.off + a] != sm->hdr[so + td.off + b]) rc = 1;
+          do { a--; } while (FWSQ(hdr[so + ti.off + a]));
+          do { b--; } while (FWSQ(hdr[so + td.off + b]));
+          if (hdr[so + ti.off + a] != hdr[so + td.off + b]) rc = 1;
         }
       }
       if (rc == 0 && (seen & (1u << T_X))) {                         // x=: plain decimal clearly in the future of `now`
         long long x = 0;
         uint32_t digits = 0;
         for (uint32_t i = 0; i < tx.len && rc == 0; i++) {
-          const uint32_t c = sm->hdr[so + tx.off + i];
+          const uint32_t c = hdr[so + tx.off + i];
           if (FWSQ(c)) continue;
           if (c < '0' || c > '9' || ++digits > 17) rc = 1;
           else x = x * 10 + (long long)(c - '0');
@@ -363,7 +360,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
         uint32_t digits = 0, plus = 0;
         unsigned long long v = 0;
         for (uint32_t i = 0; i < tl.len && rc == 0; i++) {
-          const uint32_t c = sm->hdr[so + tl.off + i];
+          const uint32_t c = hdr[so + tl.off + i];
           if (FWSQ(c)) continue;
           if (c == '+' && digits == 0 && plus == 0) { plus = 1; continue; }
           if (c < '0' || c > '9' || ++digits > 18) rc = 1;
@@ -381,7 +378,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
         const uint32_t i = base + lane;
         uint32_t c = 0;
         bool keep = false;
-        if (i < td.len) { c = sm->hdr[so + td.off + i]; keep = !FWSQ(c); }
+        if (i < td.len) { c = hdr[so + td.off + i]; keep = !FWSQ(c); }
         const unsigned m = __ballot_sync(FULL, keep);
         const uint32_t r = j + __popc(m & ltm);
         if (keep) differ = differ || r >= dom_len || LOW(c) != LOW(dom[r]);
@@ -421,7 +418,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
     const uint32_t i = base + lane;
     uint32_t c = 0;
     bool keep = false;
-    if (i < th.len) { c = sm->hdr[so + th.off + i]; keep = !FWSQ(c); }
+    if (i < th.len) { c = hdr[so + th.off + i]; keep = !FWSQ(c); }
     const unsigned m = __ballot_sync(FULL, keep);
     const uint32_t r = hl + __popc(m & ltm);
     if (keep && r < sizeof sm->hbuf) sm->hbuf[r] = (uint8_t)c;
@@ -488,7 +485,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
     }
     if (hit >= 0) {
       bool eq = true;
-      for (uint32_t t = lane; t < nl; t += 32) eq = eq && LOW(sm->hdr[sm->hstart[hit] + t]) == LOW(sm->hbuf[sm->name_s[j] + t]);
+      for (uint32_t t = lane; t < nl; t += 32) eq = eq && LOW(hdr[sm->hstart[hit] + t]) == LOW(sm->hbuf[sm->name_s[j] + t]);
       if (__ballot_sync(FULL, !eq)) FE_FAIL(FE_FALLBACK);
     }
     if (lane == 0) sm->hit_of[j] = (int16_t)hit;
@@ -505,7 +502,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
   };
   auto put_raw = [&](uint32_t off, uint32_t len, bool lower) {
     for (uint32_t t = lane; t < len; t += 32) {
-      const uint32_t c = sm->hdr[off + t];
+      const uint32_t c = hdr[off + t];
       if (o + t < FE_PRE_CAP) pre[o + t] = (uint8_t)(lower ? LOW(c) : c); else overflow = true;
     }
     o += len;
@@ -522,7 +519,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
       uint32_t c = 0;
       bool present = false, wsp = false;
       if (i < len && !(i >= skip_lo && i < skip_hi)) {
-        c = sm->hdr[off + i];
+        c = hdr[off + i];
         present = c != '\r' && c != '\n';
         wsp = c == ' ' || c == '\t';
       }
@@ -566,11 +563,11 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
   // text anywhere in the value is left to the host
   {
     bool dup = false;
-    const uint32_t b0 = sm->hdr[so + tb.off];
+    const uint32_t b0 = hdr[so + tb.off];
     for (uint32_t p = lane; p + tb.len <= sn; p += 32) {
-      if (p == tb.off || sm->hdr[so + p] != b0) continue;
+      if (p == tb.off || hdr[so + p] != b0) continue;
       bool same = true;
-      for (uint32_t t = 1; same && t < tb.len; t++) same = sm->hdr[so + p + t] == sm->hdr[so + tb.off + t];
+      for (uint32_t t = 1; same && t < tb.len; t++) same = hdr[so + p + t] == hdr[so + tb.off + t];
       dup = dup || same;
     }
     if (__ballot_sync(FULL, dup)) FE_FAIL(FE_FALLBACK);
@@ -600,7 +597,7 @@ __device__ inline void fe_process_warp(FeWarpSmem* sm, const FeLut* lut, const u
       const uint32_t i = base + lane;
       uint32_t c = 0;
       bool keep = false;
-      if (i < v.len) { c = sm->hdr[so + v.off + i]; keep = !FWSQ(c); }
+      if (i < v.len) { c = hdr[so + v.off + i]; keep = !FWSQ(c); }
       const unsigned m = __ballot_sync(FULL, keep);
       const uint32_t r = cnt + __popc(m & ltm);
       if (keep && r < FE_B64_CAP) sm->b64[r] = (uint8_t)c;
