@@ -21,6 +21,10 @@ void launch_rsa64(bool generic, int lanes, const uint32_t* sig_arena, const RsaI
     // e = 65537, four lanes per signature: the variant with the dedicated squaring (Mont::sqr), 64-thread CTAs
     const unsigned block = 64;
     const unsigned grid = (unsigned)(((uint64_t)n * 4 + block - 1) / block);
+    // 27 KB of shared memory per CTA: ask for the largest carve-out, otherwise shared memory (not registers) caps the
+    // kernel at 6 CTAs per SM (ncu: launch__occupancy_limit_shared_mem)
+    static bool carve = false;
+    if (!carve) { cudaFuncSetAttribute(rsa_verify_kernel<64, 4, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); carve = true; }
     rsa_verify_kernel<64, 4, false, true><<<grid, block, 0, s>>>(sig_arena, items, n, keytab, digests, cand_flags);
     return;
   }
