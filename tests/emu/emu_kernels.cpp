@@ -27,12 +27,13 @@ static void run_rsa(const uint32_t* sig_arena, const RsaItem* items, uint32_t n_
   });
 }
 
+template <int V>
 static void run_rsa_sqr(const uint32_t* sig_arena, const RsaItem* items, uint32_t n_items,
                         const uint32_t* keytab, const uint32_t* digests, uint32_t* flags) {
   const unsigned block = 64;
   unsigned threads = n_items * 4;
   emu::launch((threads + block - 1) / block, block, [&]() {
-    rsa_verify_kernel<64, 4, false, true>(sig_arena, items, n_items, keytab, digests, flags);
+    rsa_verify_kernel<64, 4, false, V>(sig_arena, items, n_items, keytab, digests, flags);
   });
 }
 
@@ -64,7 +65,8 @@ int emu_rsa_verify(int limbs, int T, int generic, const uint32_t* sig_arena, con
                    uint32_t n_items, const uint32_t* keytab, const uint32_t* digests,
                    uint32_t* flags) {
   const RsaItem* it = (const RsaItem*)items;
-  if (limbs == 64 && T == 104 && !generic) { run_rsa_sqr(sig_arena, it, n_items, keytab, digests, flags); return 0; }   // T = 104: the squaring variant
+  if (limbs == 64 && T == 104 && !generic) { run_rsa_sqr<8>(sig_arena, it, n_items, keytab, digests, flags); return 0; }   // T = 104: the squaring variant
+  if (limbs == 64 && T == 204 && !generic) { run_rsa_sqr<104>(sig_arena, it, n_items, keytab, digests, flags); return 0; }  // T = 204: with the rolled combine
 #define CASE(LB, TT)                                                                        \
   if (limbs == LB && T == TT) {                                                             \
     if (generic) run_rsa<LB, TT, true>(sig_arena, it, n_items, keytab, digests, flags);     \

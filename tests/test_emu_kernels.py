@@ -95,6 +95,7 @@ def test_rsa_kernel_source_with_dedicated_squaring():
             exp.append(1 if oracle.rsa_verify_sha256(der, h, ss[-1]) == 1 else 0)
         assert exp[0] == 1 and exp[1] == 0
         assert emu.rsa_verify(ks, ds, ss, 64, 104) == exp, nbits
+        assert emu.rsa_verify(ks, ds, ss, 64, 204) == exp, nbits
 
 
 def _prime(bits, rng):

@@ -1,5 +1,9 @@
 #include "kernels.h"
 #include "rsa.cuh"
+#include <cstdlib>
+#ifndef ZKB_SQR_DEFAULT
+#define ZKB_SQR_DEFAULT 8
+#endif
 namespace zkb {
 template <bool G>
 static void launch_t(int lanes, const uint32_t* sig_arena, const RsaItem* items, uint32_t n, const uint32_t* keytab,
@@ -22,10 +26,19 @@ void launch_rsa64(bool generic, int lanes, const uint32_t* sig_arena, const RsaI
     const unsigned block = 64;
     const unsigned grid = (unsigned)(((uint64_t)n * 4 + block - 1) / block);
     // 27 KB of shared memory per CTA: ask for the largest carve-out, otherwise shared memory (not registers) caps the
-    // kernel at 6 CTAs per SM (ncu: launch__occupancy_limit_shared_mem)
-    static bool carve = false;
-    if (!carve) { cudaFuncSetAttribute(rsa_verify_kernel<64, 4, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); carve = true; }
-    rsa_verify_kernel<64, 4, false, true><<<grid, block, 0, s>>>(sig_arena, items, n, keytab, digests, cand_flags);
+    // kernel at 6 CTAs per SM (ncu: launch__occupancy_limit_shared_mem).  ZKB_SQR_VARIANT picks one of the instantiated
+    // code-shape variants (see rsa.cuh) for A/B runs.
+    static int variant = -1;
+    if (variant < 0) { const char* v = getenv("ZKB_SQR_VARIANT"); variant = v ? atoi(v) : ZKB_SQR_DEFAULT; }
+#define ZKB_SQR_CASE(V)                                                                                             \
+  case V: {                                                                                                         \
+    static bool carve = false;                                                                                      \
+    if (!carve) { cudaFuncSetAttribute(rsa_verify_kernel<64, 4, false, V>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); carve = true; } \
+    rsa_verify_kernel<64, 4, false, V><<<grid, block, 0, s>>>(sig_arena, items, n, keytab, digests, cand_flags);    \
+    break;                                                                                                          \
+  }
+    switch (variant) { ZKB_SQR_CASE(4) ZKB_SQR_CASE(16) ZKB_SQR_CASE(104) ZKB_SQR_CASE(108) ZKB_SQR_CASE(116) ZKB_SQR_CASE(1008) ZKB_SQR_CASE(2008) ZKB_SQR_CASE(1108) ZKB_SQR_CASE(1004) default: ZKB_SQR_CASE(8) }
+#undef ZKB_SQR_CASE
     return;
   }
   if (generic) launch_t<true>(lanes, sig_arena, items, n, keytab, digests, cand_flags, s);

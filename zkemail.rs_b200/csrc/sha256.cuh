@@ -91,9 +91,6 @@ sha256_batch_kernel(const uint8_t* __restrict__ arena, const uint64_t* __restric
       uint4 v0, v1, v2, v3;
       if (PREFETCH) {
         v0 = n0; v1 = n1; v2 = n2; v3 = n3;
-        if (blk < nfull) {
-          n0 = __ldg(p + 4 * blk + 4); n1 = __ldg(p + 4 * blk + 5); n2 = __ldg(p + 4 * blk + 6); n3 = __ldg(p + 4 * blk + 7);
-        }
       } else {
         v0 = __ldg(p + 4 * blk); v1 = __ldg(p + 4 * blk + 1); v2 = __ldg(p + 4 * blk + 2); v3 = __ldg(p + 4 * blk + 3);
       }
@@ -101,6 +98,12 @@ sha256_batch_kernel(const uint8_t* __restrict__ arena, const uint64_t* __restric
       w[4] = bswap32(v1.x); w[5] = bswap32(v1.y); w[6] = bswap32(v1.z); w[7] = bswap32(v1.w);
       w[8] = bswap32(v2.x); w[9] = bswap32(v2.y); w[10] = bswap32(v2.z); w[11] = bswap32(v2.w);
       w[12] = bswap32(v3.x); w[13] = bswap32(v3.y); w[14] = bswap32(v3.z); w[15] = bswap32(v3.w);
+    }
+    if (PREFETCH) {
+      // unconditional (a predicated load made ptxas copy the sixteen registers around it and wait for the load at once):
+      // past the last readable block the index is clamped and the bytes are ignored
+      const uint32_t nx = blk < nfull ? blk + 1 : nfull;
+      n0 = __ldg(p + 4 * nx); n1 = __ldg(p + 4 * nx + 1); n2 = __ldg(p + 4 * nx + 2); n3 = __ldg(p + 4 * nx + 3);
     }
     if (blk >= nfull) {  // tail: mask bytes past the end, append 0x80 / zeros / bit length
 #pragma unroll
