@@ -201,7 +201,7 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-extras", action="store_true", help="only value + e2e (no with_regex / value_from_raw / e2e_registered)")
     ap.add_argument("--profile", action="store_true", help="engine flag ZKB_OPT_PROFILE: per-call host / stream breakdown on stderr")
-    ap.add_argument("--sqr", action="store_true", help="engine flag ZKB_OPT_SQR: RSA-2048 kernel variant with the dedicated Montgomery squaring (A/B)")
+    ap.add_argument("--no-sqr", action="store_true", help="engine flag ZKB_OPT_NO_SQR: the plain RSA-2048 kernel instead of the one with the dedicated Montgomery squaring (A/B)")
     ap.add_argument("--seed", type=int, default=0xD1C1)
     args = ap.parse_args()
 
@@ -290,7 +290,7 @@ def main():
 
     pool, order = build_pool(pool_wl, n_emails, args.unique, args.seed + 7919 * rank, threads, log)
     eng = z.Engine(device=local_rank, host_threads=threads, now_unix=NOW, chunk_emails=args.chunk,
-                   rsa_lanes=args.rsa_lanes, flags=(z.OPT_PROFILE if args.profile else 0) | (z.OPT_SQR if args.sqr else 0))
+                   rsa_lanes=args.rsa_lanes, flags=(z.OPT_PROFILE if args.profile else 0) | (z.OPT_NO_SQR if args.no_sqr else 0))
     views_np = pool.engine_views(order)
     views = EmailViews.from_arrays(views_np, keep=pool)
     exp_ok = pool.expected_ok()[order]
@@ -471,7 +471,7 @@ def main():
     rsa_alg = stats["rsa_macs"]
     # executed IMAD.WIDE per signature: a multiplication of the interleaved loop is 2 l^2; a dedicated squaring of the
     # 2048-bit kernel is l(l+1)/2 + l^2 = 6176 (16 of the 18 multiplications when four lanes work on a signature)
-    sqr_on = args.sqr and (args.rsa_lanes or 4) == 4
+    sqr_on = (not args.no_sqr) and (args.rsa_lanes or 4) == 4
     rsa_exec = (stats["rsa_items_2048"] * ((2 * 8192 + 16 * 6176) if sqr_on else 18 * 8192) + stats["rsa_items_1024"] * 18 * 2048
                 + stats["rsa_items_other"] * 18 * 32768)
     sha_ops = stats["sha_blocks"] * 1400

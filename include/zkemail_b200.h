@@ -110,8 +110,8 @@ enum {
   ZKB_OPT_NO_STAGED_FRONTEND = 4u, /* pageable callers: host front end instead of staging raw bytes for the device  */
   ZKB_OPT_NO_OVERLAP = 8u,         /* resident batches: one stream instead of the two-stream schedule               */
   ZKB_OPT_PROFILE = 16u,           /* per-call host / stream time breakdown on stderr                               */
-  ZKB_OPT_SQR = 32u,               /* RSA-2048, e = 65537: the kernel variant with the dedicated Montgomery squaring (fewer
-                                      multiply-accumulates, measured slower on B200: DESIGN.md section 3; off by default) */
+  ZKB_OPT_NO_SQR = 32u,            /* RSA-2048, e = 65537, four lanes: the plain kernel (18 interleaved multiplications)
+                                      instead of the one with the dedicated Montgomery squaring */
   ZKB_OPT_ALL = 63u
 };
 

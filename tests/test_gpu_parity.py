@@ -277,12 +277,12 @@ def test_raw_resident_batches_redo_the_front_end_every_run(engine):
 
 
 def test_rsa_kernel_variant_with_dedicated_squaring():
-    """ZKB_OPT_SQR: rsa_verify_kernel<64, 4, false, SQR> (Mont::sqr for the 16 squarings of s^65537).  Same verdicts as the
-    default kernel and the oracle on forged / flipped / out-of-range signatures, and on a mixed batch end to end."""
+    """rsa_verify_kernel<64, 4, false, SQR> (Mont::sqr for the 16 squarings of s^65537, the default) against the plain
+    kernel (ZKB_OPT_NO_SQR).  Same verdicts as the plain kernel and the oracle on forged / flipped / out-of-range signatures, and on a mixed batch end to end."""
     from cryptography.hazmat.primitives import hashes
     from cryptography.hazmat.primitives.asymmetric import padding
-    eng = z.Engine(flags=z.OPT_SQR, now_unix=NOW)
-    ref = z.Engine(now_unix=NOW)
+    eng = z.Engine(now_unix=NOW)
+    ref = z.Engine(flags=z.OPT_NO_SQR, now_unix=NOW)
     try:
         keys = key_pool()[2048]
         ks, ds, ss = [], [], []

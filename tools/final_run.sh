@@ -16,4 +16,4 @@ print(d["value_from_raw"]["kernel_ms"]); print("config equal:", r["config"] == d
 PY
 CMD="python bench.py --emails 262144 --steps 2 --warmup 3 --skip-cpu-baseline"
 $CMD > gpurun_out/final_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_r2_final.csv $CMD > gpurun_out/final_ncu1.log 2>&1; echo "ncu list rc=$?"
-$CMD > gpurun_out/final_plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'frontend_warp' -s 2 -c 1 -o gpurun_out/prof_fe_final $CMD > gpurun_out/final_ncu2.log 2>&1; echo "ncu fe rc=$?"
+$CMD > gpurun_out/final_plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'rsa_verify|sha256_batch|assemble|frontend_warp|canon_body_staged|dfa_scan|bh_check' -s 40 -c 14 -o gpurun_out/prof_all_final $CMD > gpurun_out/final_ncu2.log 2>&1; echo "ncu all rc=$?"

@@ -7,7 +7,7 @@ from .structs import (  # noqa: F401
 from .engine import (  # noqa: F401,E402
     Engine, EngineUnavailable, RegexError, RegexSet, VerificationPanic, compile_regex,
     canonicalize_signed_email, compile_regex_parts, verify_email, verify_email_with_regex,
-    OPT_NO_DIRECT, OPT_NO_DEVICE_FRONTEND, OPT_NO_STAGED_FRONTEND, OPT_NO_OVERLAP, OPT_PROFILE, OPT_SQR,
+    OPT_NO_DIRECT, OPT_NO_DEVICE_FRONTEND, OPT_NO_STAGED_FRONTEND, OPT_NO_OVERLAP, OPT_PROFILE, OPT_NO_SQR,
 )
 from .abi_io import AbiDecodeError, VerificationOutput, abi_decode, abi_encode_batch  # noqa: F401,E402
 from .generator import (  # noqa: F401,E402

@@ -1156,7 +1156,7 @@ int launch_chunk(zkb_engine* e, const DeviceChunk& d, const zkb_regex_set* rs, c
     const bool generic = (k & 1) != 0;
     switch (k >> 1) {
       case 0: launch_rsa32(generic, std::max(2, lanes / 2), d.sig_arena, d.rsa_items[k], d.rsa_n[k], e->d_keytab, d.digests, d.cand_flags, s); break;
-      case 1: launch_rsa64(generic, lanes, d.sig_arena, d.rsa_items[k], d.rsa_n[k], e->d_keytab, d.digests, d.cand_flags, s, e->has(ZKB_OPT_SQR)); break;
+      case 1: launch_rsa64(generic, lanes, d.sig_arena, d.rsa_items[k], d.rsa_n[k], e->d_keytab, d.digests, d.cand_flags, s, !e->has(ZKB_OPT_NO_SQR)); break;
       default: launch_rsa128(generic, std::min(16, lanes * 2), d.sig_arena, d.rsa_items[k], d.rsa_n[k], e->d_keytab, d.digests, d.cand_flags, s); break;
     }
     nl++;

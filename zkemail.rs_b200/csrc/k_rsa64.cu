@@ -26,18 +26,23 @@ void launch_rsa64(bool generic, int lanes, const uint32_t* sig_arena, const RsaI
     const unsigned block = 64;
     const unsigned grid = (unsigned)(((uint64_t)n * 4 + block - 1) / block);
     // 27 KB of shared memory per CTA: ask for the largest carve-out, otherwise shared memory (not registers) caps the
-    // kernel at 6 CTAs per SM (ncu: launch__occupancy_limit_shared_mem).  ZKB_SQR_VARIANT picks one of the instantiated
-    // code-shape variants (see rsa.cuh) for A/B runs.
-    static int variant = -1;
-    if (variant < 0) { const char* v = getenv("ZKB_SQR_VARIANT"); variant = v ? atoi(v) : ZKB_SQR_DEFAULT; }
+    // kernel at 6 CTAs per SM (ncu: launch__occupancy_limit_shared_mem).
 #define ZKB_SQR_CASE(V)                                                                                             \
   case V: {                                                                                                         \
-    static bool carve = false;                                                                                      \
-    if (!carve) { cudaFuncSetAttribute(rsa_verify_kernel<64, 4, false, V>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); carve = true; } \
+    /* a per-device attribute: set at every launch (engines of several devices share this code) */                  \
+    cudaFuncSetAttribute(rsa_verify_kernel<64, 4, false, V>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);  \
     rsa_verify_kernel<64, 4, false, V><<<grid, block, 0, s>>>(sig_arena, items, n, keytab, digests, cand_flags);    \
     break;                                                                                                          \
   }
-    switch (variant) { ZKB_SQR_CASE(4) ZKB_SQR_CASE(16) ZKB_SQR_CASE(104) ZKB_SQR_CASE(108) ZKB_SQR_CASE(116) ZKB_SQR_CASE(1008) ZKB_SQR_CASE(2008) ZKB_SQR_CASE(1108) ZKB_SQR_CASE(1004) default: ZKB_SQR_CASE(8) }
+#ifdef ZKB_SQR_EXPERIMENTS
+    // A/B builds only (make EXTRA=-DZKB_SQR_EXPERIMENTS): ZKB_SQR_VARIANT picks one of the code-shape variants of rsa.cuh.
+    // The product library instantiates the measured best one and reads no environment variables.
+    static int variant = -1;
+    if (variant < 0) { const char* v = getenv("ZKB_SQR_VARIANT"); variant = v ? atoi(v) : ZKB_SQR_DEFAULT; }
+    switch (variant) { ZKB_SQR_CASE(4) ZKB_SQR_CASE(16) ZKB_SQR_CASE(104) ZKB_SQR_CASE(108) ZKB_SQR_CASE(1008) ZKB_SQR_CASE(2008) default: ZKB_SQR_CASE(8) }
+#else
+    switch (ZKB_SQR_DEFAULT) { default: ZKB_SQR_CASE(ZKB_SQR_DEFAULT) }
+#endif
 #undef ZKB_SQR_CASE
     return;
   }

@@ -154,7 +154,7 @@ EXPORTED_SYMBOLS = (
 )
 
 # zkb_options.flags / zkb_engine_set_flags (include/zkemail_b200.h)
-OPT_NO_DIRECT, OPT_NO_DEVICE_FRONTEND, OPT_NO_STAGED_FRONTEND, OPT_NO_OVERLAP, OPT_PROFILE, OPT_SQR = 1, 2, 4, 8, 16, 32
+OPT_NO_DIRECT, OPT_NO_DEVICE_FRONTEND, OPT_NO_STAGED_FRONTEND, OPT_NO_OVERLAP, OPT_PROFILE, OPT_NO_SQR = 1, 2, 4, 8, 16, 32
 
 _lib = None
 
