@@ -95,19 +95,20 @@ def _slot_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_record_slot_allgather_world2_gloo():
+@pytest.mark.parametrize("world", [2, 3])
+def test_record_slot_allgather_gloo(world):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    ps = [ctx.Process(target=_slot_worker, args=(r, 2, port, q)) for r in range(2)]
+    ps = [ctx.Process(target=_slot_worker, args=(r, world, port, q)) for r in range(world)]
     for p in ps:
         p.start()
     res = [q.get(timeout=180) for _ in ps]
     for p in ps:
         p.join(timeout=60)
-    assert sorted(r[:2] for r in res) == [(0, True), (1, True)]
-    assert res[0][2][0] > res[0][2][1]      # unequal shard sizes were exercised
+    assert sorted(r[:2] for r in res) == [(r, True) for r in range(world)]
+    assert res[0][2][0] > res[0][2][-1]      # unequal shard sizes were exercised
 
 
 # ------------------------------------------------------------------ GPU
