@@ -300,7 +300,7 @@ def main():
     stream = torch.cuda.ExternalStream(eng.lib.zkb_engine_stream(eng.handle), device=dev)
     clocks = ClockSampler(local_rank)
     # multi-GPU: the one exchange of the path is the all-gather of the fixed-size result records, issued by the
-    # library itself (ncclAllGather on the engine stream, csrc/engine_multi.inc); torch.distributed only carries the id
+    # library itself (ncclSend / ncclRecv per resident chunk beside the next chunk's kernels, csrc/engine_multi.inc); torch.distributed only carries the id
     comm = z.Comm(eng, rank, world) if dist is not None else None
 
     t0 = time.time()
@@ -312,9 +312,10 @@ def main():
         """W warm-up steps, then K timed steps (CUDA events on the engine stream, barrier + synchronize on both sides,
         max over ranks).  Every step ends with the record all-gather when there are several ranks."""
         def step():
-            pb.run_async()
             if comm is not None:
-                comm.allgather_records(pb)
+                comm.last = comm.run_allgather(pb)     # the kernels + the record exchange, chunk k's records travelling under chunk k + 1
+            else:
+                pb.run_async()
         for _ in range(W):
             step()
         barrier()
@@ -329,6 +330,24 @@ def main():
         res = pb.fetch()   # the verdicts of the timed schedule against the generator's ground truth
         bad = int(((res["status"] == 0) != exp_ok).sum())
         assert bad == 0, f"{label}: {bad} verdicts differ from the generator's ground truth"
+        if comm is not None:
+            # what the exchange delivered: every rank's slot must carry that rank's verdicts (a checksum per rank,
+            # compared through torch.distributed, outside the timed region)
+            ptr, slot, rb = comm.last
+            counts = comm.rank_records()
+            got = torch.empty((world, slot, rb), dtype=torch.uint8, device=dev)
+            import ctypes as C
+            rt = C.CDLL("libcudart.so.12")
+            assert rt.cudaMemcpy(C.c_void_p(got.data_ptr()), C.c_void_p(ptr), C.c_size_t(got.numel()), 3) == 0
+            st = got[:, :, 0:4].contiguous().view(torch.int32).squeeze(-1)            # status word of every record
+            sums = torch.stack([(st[r, :counts[r]] == 0).sum() for r in range(world)]).to(torch.int64)
+            mine = torch.tensor([int((res["status"] == 0).sum())], dtype=torch.int64, device=dev)
+            allm = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allm, mine)
+            want = torch.cat(allm)
+            # records the device declined (status REDO) are finished by the host in fetch(): at most those may differ
+            redo = torch.stack([(st[r, :counts[r]] == 0x7fffffff).sum() for r in range(world)]).to(torch.int64)
+            assert bool(((want - sums) >= 0).all()) and bool(((want - sums) <= redo).all()), (label, want.tolist(), sums.tolist(), redo.tolist())
         return ms
 
     # ---- device-resident pass: batch packed + uploaded once ----
@@ -525,7 +544,7 @@ def main():
                        "l2": f"inputs larger than L2: {stats['arena_bytes'] / 1e9:.2f} GB arena per step", "host_threads": threads,
                        "value_is": "device-resident verify_email" + ("_with_regex" if main_regex else "") + " step: SHA-256 + bh= + RSA"
                                    + (" + DFA scans" if main_regex else "") + " + result records; value_from_raw adds the device front end and canonicalisation",
-                       "collective": "none (1 GPU)" if world == 1 else "ncclAllGather of the result records (144 B per email), issued by the library on the engine stream inside every step",
+                       "collective": "none (1 GPU)" if world == 1 else "exchange of the result records (144 B per email; ncclSend / ncclRecv issued by the library per resident chunk, overlapping the next chunk's kernels) inside every step",
                        "rsa_lanes": args.rsa_lanes or 4},
             "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_int": roofline_int, "cpu_baseline": cpu_baseline,
             "e2e": e2e, "e2e_registered": e2e_registered, "value_from_raw": value_from_raw, "with_regex": with_regex,

@@ -269,6 +269,10 @@ void zkb_comm_destroy(zkb_comm *c);
  * records.  *dev_records: world x *slot_records records of *rec_bytes bytes in this rank's device memory (rank r's
  * records start at r * slot_records; slot_records = the largest shard, shorter shards are zero padded). */
 int zkb_comm_allgather_records(zkb_comm *c, zkb_batch *b, void **dev_records, size_t *slot_records, size_t *rec_bytes);
+/* zkb_batch_run_async + the exchange of the records in one call: the records of resident chunk k travel (ncclSend / ncclRecv
+ * on a stream of the communicator) while the kernels of chunk k+1 run; same output layout as zkb_comm_allgather_records,
+ * complete in engine-stream order.  Every rank of the communicator must make the call. */
+int zkb_comm_run_allgather(zkb_comm *c, zkb_batch *b, void **dev_records, size_t *slot_records, size_t *rec_bytes);
 int zkb_comm_rank_records(const zkb_comm *c, uint64_t *counts, size_t n);   /* records held per rank */
 
 /* ---- host-only utility: cfdkim::canonicalize_signed_email (core/src/circuits.rs:34-35,

@@ -175,8 +175,10 @@ def test_multi_engine_on_two_devices():
 
 
 @pytest.mark.gpu
-def test_comm_allgather_of_resident_records_one_rank(engine):
-    """zkb_comm with a world of one: the library's NCCL path (id, communicator, count exchange, in-place all-gather)."""
+@pytest.mark.parametrize("overlapped", [False, True])
+def test_comm_allgather_of_resident_records_one_rank(engine, overlapped):
+    """zkb_comm with a world of one: the library's NCCL path (id, communicator, count exchange, in-place all-gather) and the
+    run + exchange call (chunk table, exchange stream; no peers to send to)."""
     import ctypes as C
     emails, _ = mixed_emails(seed=52, n_pos=40)
     views = EmailViews.from_emails(emails)
@@ -184,8 +186,11 @@ def test_comm_allgather_of_resident_records_one_rank(engine):
     try:
         for raw in (False, True):
             pb = engine.prepare(views, raw=raw)
-            pb.run_async()
-            ptr, slot, rb = comm.allgather_records(pb)
+            if overlapped:
+                ptr, slot, rb = comm.run_allgather(pb)
+            else:
+                pb.run_async()
+                ptr, slot, rb = comm.allgather_records(pb)
             res = pb.fetch()                      # synchronises the engine stream
             assert slot == len(emails) and rb == 144 and comm.rank_records() == [len(emails)]
             host = np.zeros((slot, rb), dtype=np.uint8)
@@ -198,3 +203,71 @@ def test_comm_allgather_of_resident_records_one_rank(engine):
             pb.close()
     finally:
         comm.close()
+
+
+def _comm_worker(rank, world, port, q):
+    """One process per GPU: ranks hold different shards in different numbers of chunks; every rank must end up with every
+    rank's records, byte for byte what the owner fetched."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    try:
+        import ctypes as C
+        import torch.distributed as dist
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        import zkemail_rs_b200 as zz
+        from tests.util import mixed_emails as mk, NOW as now
+        emails, _ = mk(seed=60, n_pos=120)
+        lo, hi = (0, len(emails) // 3) if rank == 0 else (len(emails) // 3, len(emails))
+        eng = zz.Engine(device=rank, now_unix=now, chunk_emails=8)          # resident chunks of 32 emails: 2 and 3 exchange rounds
+        comm = zz.Comm(eng, rank, world)
+        from zkemail_rs_b200.engine import EmailViews as EV
+        views = EV.from_emails(emails[lo:hi])
+        ok = True
+        rt = C.CDLL("libcudart.so.12")
+        for overlapped in (True, False, True):
+            pb = eng.prepare(views, raw=True)
+            if overlapped:
+                ptr, slot, rb = comm.run_allgather(pb)
+            else:
+                pb.run_async()
+                ptr, slot, rb = comm.allgather_records(pb)
+            mine = pb.fetch()
+            counts = comm.rank_records()
+            host = np.zeros((world, slot, rb), dtype=np.uint8)
+            ok = ok and rt.cudaSetDevice(rank) == 0
+            ok = ok and rt.cudaMemcpy(C.c_void_p(host.ctypes.data), C.c_void_p(ptr), C.c_size_t(host.nbytes), 2) == 0
+            own = [bytes(host[rank, i]) for i in range(counts[rank])]
+            box = [None] * world
+            dist.all_gather_object(box, own)
+            for r in range(world):
+                ok = ok and counts[r] == len(box[r]) and not host[r, counts[r]:].any()
+                for i in range(counts[r]):
+                    ok = ok and bytes(host[r, i]) == box[r][i]
+            for i, m in enumerate(mine):                                     # and the owner's slot is what fetch() returns
+                if int.from_bytes(own[i][:4], "little", signed=True) != 0x7fffffff:
+                    ok = ok and own[i] == m.tobytes()[:rb]
+            pb.close()
+        q.put((rank, bool(ok), counts))
+        comm.close()
+        eng.close()
+        dist.destroy_process_group()
+    except Exception as ex:   # noqa: BLE001
+        q.put((rank, False, repr(ex)))
+
+
+@pytest.mark.gpu
+def test_comm_run_allgather_two_ranks():
+    if _device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_comm_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=600) for _ in ps]
+    for p in ps:
+        p.join(timeout=120)
+    assert sorted(r[:2] for r in res) == [(0, True), (1, True)], res

@@ -1935,21 +1935,24 @@ int zkb_batch_prepare_raw(zkb_engine* e, const zkb_email_view* emails, size_t n,
   return batch_prepare_impl(e, emails, n, regex, captures, out, true);
 }
 
-int zkb_batch_run_async(zkb_batch* b) {
-  if (!b) return ZKB_E_INVALID;
+// The enqueue of zkb_batch_run_async with e->run_mu held.  after_chunk(k, s), if given, runs once the last kernel of
+// resident chunk k (the one that writes its result records) has been enqueued on stream s (zkb_comm_run_allgather hooks
+// the exchange of that chunk's records there).
+using AfterChunk = std::function<int(size_t, cudaStream_t)>;
+static int batch_run_async_locked(zkb_batch* b, const AfterChunk* after_chunk) {
   zkb_engine* e = b->eng;
-  std::lock_guard<std::mutex> lock(e->run_mu);   // enqueue only; serialised with the other calls on this engine
   CK(cudaSetDevice(e->device));
   cudaStream_t s = e->slots[0].stream;
   const size_t nc = b->dev.size();
   if (nc < 2 || e->has(ZKB_OPT_NO_OVERLAP)) {
-    for (auto* d : b->dev) {
+    for (auto& d : b->dev) {
       // flags and DFA outputs accumulate with atomicOr / plain stores: reset them for a re-run
       size_t o_flags, o_dfa;
       out_layout(d->M, d->C, d->NE, d->P, o_flags, o_dfa);
       CK(cudaMemsetAsync(d->out.p + o_flags, 0, align_up((size_t)d->C * 4, 16), s));
       int rc = launch_chunk(e, *d, b->regex, s, nullptr, nullptr);
       if (rc) return rc;
+      if (after_chunk && (rc = (*after_chunk)((size_t)(&d - &b->dev[0]), s)) != 0) return rc;
     }
     b->ran = true;
     return ZKB_OK;
@@ -1980,11 +1983,18 @@ int zkb_batch_run_async(zkb_batch* b) {
     CK(cudaStreamWaitEvent(s, e->ev_pre[k], 0));
     rc = launch_chunk(e, *d, b->regex, s, nullptr, nullptr, 2);
     if (rc) return rc;
+    if (after_chunk && (rc = (*after_chunk)(k, s)) != 0) return rc;
   }
   CK(cudaEventRecord(e->ev_join, aux));
   CK(cudaStreamWaitEvent(s, e->ev_join, 0));
   b->ran = true;
   return ZKB_OK;
+}
+
+int zkb_batch_run_async(zkb_batch* b) {
+  if (!b) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lock(b->eng->run_mu);   // enqueue only; serialised with the other calls on this engine
+  return batch_run_async_locked(b, nullptr);
 }
 
 int zkb_batch_run(zkb_batch* b) {

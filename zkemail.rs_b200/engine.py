@@ -149,7 +149,7 @@ EXPORTED_SYMBOLS = (
     "zkb_plan_shards", "zkb_multi_create", "zkb_multi_destroy", "zkb_multi_devices", "zkb_multi_engine", "zkb_multi_host_register",
     "zkb_multi_host_unregister", "zkb_multi_regex_set_create", "zkb_multi_regex_destroy", "zkb_multi_verify_batch",
     "zkb_multi_batch_prepare", "zkb_multi_batch_run", "zkb_multi_batch_fetch", "zkb_multi_batch_bounds", "zkb_multi_batch_gathered",
-    "zkb_multi_batch_destroy", "zkb_comm_unique_id", "zkb_comm_create", "zkb_comm_destroy", "zkb_comm_allgather_records",
+    "zkb_multi_batch_destroy", "zkb_comm_unique_id", "zkb_comm_create", "zkb_comm_destroy", "zkb_comm_allgather_records", "zkb_comm_run_allgather",
     "zkb_comm_rank_records",
 )
 

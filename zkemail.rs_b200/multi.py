@@ -22,9 +22,28 @@ COMM_ID_BYTES = 128
 REC_HEAD = 144   # offsetof(zkb_result, parts)
 
 
+def _preload_nccl():
+    """The C library opens NCCL by its SONAME at the first multi-GPU call.  In a Python process that may import torch LATER,
+    the system libnccl.so.2 must not be the copy that gets mapped: torch's libtorch_cuda.so needs the (newer) NCCL its wheel
+    bundles and the loader would hand it the one already mapped (ImportError: undefined symbol).  So the bundled copy, if
+    there is one, is mapped first; non-Python callers just get the system library."""
+    try:
+        import glob
+        import importlib.util
+        import os
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            for f in sorted(glob.glob(os.path.join(d, "lib", "libnccl.so*"))):
+                C.CDLL(f, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:   # noqa: BLE001  (no bundled copy / not loadable: the SONAME lookup of the C library decides)
+        pass
+
+
 def _bind(L):
     if getattr(L, "_multi_bound", False):
         return L
+    _preload_nccl()
     vp, sz = C.c_void_p, C.c_size_t
     L.zkb_plan_shards.argtypes = [vp, sz, sz, C.c_int, C.POINTER(sz)]
     L.zkb_multi_create.argtypes = [C.POINTER(_Options), C.POINTER(C.c_int32), sz, C.POINTER(vp)]
@@ -52,6 +71,7 @@ def _bind(L):
     L.zkb_comm_destroy.argtypes = [vp]
     L.zkb_comm_destroy.restype = None
     L.zkb_comm_allgather_records.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
+    L.zkb_comm_run_allgather.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
     L.zkb_comm_rank_records.argtypes = [vp, C.POINTER(C.c_uint64), sz]
     L._multi_bound = True
     return L
@@ -232,6 +252,14 @@ class Comm:
         p, slot, rb = C.c_void_p(), C.c_size_t(), C.c_size_t()
         _check(self.lib.zkb_comm_allgather_records(self.handle, batch.handle, C.byref(p), C.byref(slot), C.byref(rb)),
                "zkb_comm_allgather_records")
+        return p.value, slot.value, rb.value
+
+    def run_allgather(self, batch: PreparedBatch):
+        """batch.run_async() and the exchange of the records in one call: chunk k's records travel while chunk k + 1 is
+        computed.  Same return value as allgather_records; every rank must call it."""
+        p, slot, rb = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        _check(self.lib.zkb_comm_run_allgather(self.handle, batch.handle, C.byref(p), C.byref(slot), C.byref(rb)),
+               "zkb_comm_run_allgather")
         return p.value, slot.value, rb.value
 
     def rank_records(self) -> List[int]:
