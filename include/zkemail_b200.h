@@ -271,7 +271,8 @@ void zkb_comm_destroy(zkb_comm *c);
 int zkb_comm_allgather_records(zkb_comm *c, zkb_batch *b, void **dev_records, size_t *slot_records, size_t *rec_bytes);
 /* zkb_batch_run_async + the exchange of the records in one call: the records of resident chunk k travel (ncclSend / ncclRecv
  * on a stream of the communicator) while the kernels of chunk k+1 run; same output layout as zkb_comm_allgather_records,
- * complete in engine-stream order.  Every rank of the communicator must make the call. */
+ * complete in engine-stream order.  A collective: every rank of the communicator makes the call, and all ranks switch to a
+ * newly prepared batch in the same call (the first call with a batch exchanges the ranks' chunk sizes). */
 int zkb_comm_run_allgather(zkb_comm *c, zkb_batch *b, void **dev_records, size_t *slot_records, size_t *rec_bytes);
 int zkb_comm_rank_records(const zkb_comm *c, uint64_t *counts, size_t n);   /* records held per rank */
 

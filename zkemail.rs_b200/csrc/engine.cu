@@ -381,6 +381,7 @@ struct zkb_batch {
   float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // sha256, rsa, dfa, bh check, whole run, front end + canonicalisation, records
   bool ran = false;
   bool raw = false;   // raw messages resident: every run redoes the device front end and the canonicalisation
+  uint64_t serial = 0;   // unique per prepared batch in this process (an address may be reused, a serial is not)
 };
 
 namespace {
@@ -1876,6 +1877,7 @@ static int batch_prepare_impl(zkb_engine* e, const zkb_email_view* emails, size_
   CK(cudaSetDevice(e->device));
   trim_keytab(e);
   zkb_batch* b = new zkb_batch();
+  { static std::atomic<uint64_t> next_serial{1}; b->serial = next_serial.fetch_add(1); }
   e->live_batches.fetch_add(1);
   b->eng = e; b->regex = regex; b->n = n; b->emails = emails; b->captures = captures;
   b->raw = raw;
