@@ -13,8 +13,10 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
-        L = C.CDLL(_LIB)
+        alt = os.environ.get("ZKB_EMU_LIB")     # e.g. a -fsanitize=thread build (tools/emu_tsan.sh): lanes are real threads
+        if not alt:
+            subprocess.check_call(["make", "-C", _HERE, "-s"])
+        L = C.CDLL(alt or _LIB)
         L.emu_regex_compile.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                         C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]
         L.emu_free.argtypes = [C.c_void_p]
