@@ -28,9 +28,10 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def sha256_batch(msgs, prefetch=False):
+def sha256_batch(msgs, prefetch=False, rot=0):
     """The SHA-256 kernel source over a packed arena (garbage in the padding), sorted order.
-    prefetch=True runs the double-buffered instantiation used for launches with few lanes."""
+    prefetch=True runs the double-buffered instantiation used for launches with few lanes; rot = 1 .. 3 the
+    instantiations that issue that many rotate families on the FMA pipe."""
     n = len(msgs)
     off, cur = [], 0
     for m in msgs:
@@ -43,7 +44,10 @@ def sha256_batch(msgs, prefetch=False):
     lena = np.array([len(m) for m in msgs], dtype=np.uint32)
     order = np.argsort(-lena.astype(np.int64), kind="stable").astype(np.uint32)
     dig = np.zeros((n, 8), dtype=np.uint32)
-    (lib().emu_sha256_batch_prefetch if prefetch else lib().emu_sha256_batch)(_p(arena), _p(offa), _p(lena), _p(order), n, _p(dig))
+    if rot:
+        lib().emu_sha256_batch_rot(_p(arena), _p(offa), _p(lena), _p(order), n, _p(dig), rot)
+    else:
+        (lib().emu_sha256_batch_prefetch if prefetch else lib().emu_sha256_batch)(_p(arena), _p(offa), _p(lena), _p(order), n, _p(dig))
     return [dig[i].astype(">u4").tobytes() for i in range(n)]
 
 

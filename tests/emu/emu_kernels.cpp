@@ -53,6 +53,17 @@ void emu_sha256_batch_prefetch(const uint8_t* arena, const uint64_t* off, const 
               [&]() { sha256_batch_kernel<true>(arena, off, len, order, n, digests, 1u); });
 }
 
+// the instantiations that issue rotates on the FMA pipe (rot = 1 .. 3 rotate families as multiply + add)
+void emu_sha256_batch_rot(const uint8_t* arena, const uint64_t* off, const uint32_t* len,
+                          const uint32_t* order, uint32_t n, uint32_t* digests, int rot) {
+  const unsigned block = 128;
+  emu::launch((n + block - 1) / block, block, [&]() {
+    if (rot == 1) sha256_batch_kernel<false, 1>(arena, off, len, order, n, digests, 1u);
+    else if (rot == 2) sha256_batch_kernel<true, 2>(arena, off, len, order, n, digests, 1u);
+    else sha256_batch_kernel<false, 3>(arena, off, len, order, n, digests, 1u);
+  });
+}
+
 // key DER -> key-table entry (ZKB_KEY_STRIDE words). returns 0 ok, 1 rejected
 int emu_build_key_entry(const uint8_t* der, size_t len, uint32_t* ent) {
   RsaKeyInfo k;

@@ -25,6 +25,10 @@ def test_sha256_kernel_source():
         got = emu.sha256_batch(msgs, prefetch=prefetch)
         for m, g in zip(msgs, got):
             assert g == hashlib.sha256(m).digest(), (len(m), prefetch)
+    for rot in (1, 2, 3):       # rotates issued on the FMA pipe (multiply by a power of two + add of the halves)
+        got = emu.sha256_batch(msgs, rot=rot)
+        for m, g in zip(msgs, got):
+            assert g == hashlib.sha256(m).digest(), (len(m), rot)
 
 
 def _rsa_cases(bits, n):

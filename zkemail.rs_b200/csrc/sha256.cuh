@@ -26,6 +26,9 @@ __device__ __constant__ uint32_t SHA_K[64] = {
     0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
     0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
 
+#ifndef ZKB_SHA_ROT_DEFAULT
+#define ZKB_SHA_ROT_DEFAULT 0
+#endif
 __device__ __forceinline__ uint32_t rotr32(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
 
@@ -42,18 +45,36 @@ __device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, uint32_t one) {
 #endif
 }
 
-// One compression; w[16] holds the big-endian message words and is clobbered.
+// A rotate issued on the FMA pipe: x * 2^(32-k) is the 64-bit value (x >> k) : (x << (32-k)) - one IMAD.WIDE - and the two
+// disjoint halves are merged with an IMAD add.  pw = one << (32 - k), built from the run-time 1 so that the compiler keeps
+// the multiplication.  3 FMA-pipe slots buy one ALU-pipe slot: worth it for as many rotates as it takes to level the pipes.
+__device__ __forceinline__ uint32_t rotr_fma(uint32_t x, uint32_t pw, uint32_t one) {
+#ifdef ZKB_HOST_EMU
+  const uint64_t p = (uint64_t)x * pw;
+  return (uint32_t)(p >> 32) * one + (uint32_t)p;
+#else
+  uint32_t d;
+  asm("{\n\t.reg .u64 p;\n\t.reg .u32 lo, hi;\n\tmul.wide.u32 p, %1, %2;\n\tmov.b64 {lo, hi}, p;\n\tmad.lo.u32 %0, hi, %3, lo;\n\t}"
+      : "=r"(d) : "r"(x), "r"(pw), "r"(one));
+  return d;
+#endif
+}
+
+// One compression; w[16] holds the big-endian message words and is clobbered.  ROT: how many of the rotate families go to
+// the FMA pipe (0 none; 1: rotr 7 of the schedule, 48 per block; 2: + rotr 17, 96 per block; 3: + rotr 6 of the rounds, 160).
+template <int ROT = ZKB_SHA_ROT_DEFAULT>
 __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16], uint32_t one) {
   uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+  const uint32_t pw7 = one << 25, pw17 = one << 15, pw6 = one << 26;
 #pragma unroll
   for (int i = 0; i < 64; i++) {
     if (i >= 16) {
       uint32_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
-      uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
-      uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+      uint32_t s0 = (ROT >= 1 ? rotr_fma(w15, pw7, one) : rotr32(w15, 7)) ^ rotr32(w15, 18) ^ (w15 >> 3);
+      uint32_t s1 = (ROT >= 2 ? rotr_fma(w2, pw17, one) : rotr32(w2, 17)) ^ rotr32(w2, 19) ^ (w2 >> 10);
       w[i & 15] = fadd(fadd(w[i & 15], s0, one), fadd(w[(i - 7) & 15], s1, one), one);
     }
-    uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+    uint32_t S1 = (ROT >= 3 ? rotr_fma(e, pw6, one) : rotr32(e, 6)) ^ rotr32(e, 11) ^ rotr32(e, 25);
     uint32_t ch = (e & f) ^ (~e & g);  // one LOP3
     uint32_t t1 = fadd(fadd(fadd(h, S1, one), ch, one), fadd(w[i & 15], SHA_K[i], one), one);
     uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
@@ -69,7 +90,7 @@ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16], 
 // PREFETCH: the 64 bytes of block b+1 are requested before block b is compressed.  Used when the launch has few
 // lanes (large bodies): with ~5 warps per scheduler the load latency at the top of every block is not hidden by
 // other warps.  Costs 16 registers, so launches with many lanes (occupancy-bound) use the plain variant.
-template <bool PREFETCH>
+template <bool PREFETCH, int ROT = ZKB_SHA_ROT_DEFAULT>
 __global__ void __launch_bounds__(128)
 sha256_batch_kernel(const uint8_t* __restrict__ arena, const uint64_t* __restrict__ msg_off,
                     const uint32_t* __restrict__ msg_len, const uint32_t* __restrict__ order,
@@ -118,7 +139,7 @@ sha256_batch_kernel(const uint8_t* __restrict__ arena, const uint64_t* __restric
       }
       if (blk == total - 1) { w[14] = len >> 29; w[15] = len << 3; }
     }
-    sha256_compress(st, w, one);
+    sha256_compress<ROT>(st, w, one);
   }
   uint4* o = reinterpret_cast<uint4*>(digests + (size_t)m * 8);
   o[0] = make_uint4(st[0], st[1], st[2], st[3]);
