@@ -248,6 +248,18 @@ def _comm_worker(rank, world, port, q):
                 if int.from_bytes(own[i][:4], "little", signed=True) != 0x7fffffff:
                     ok = ok and own[i] == m.tobytes()[:rb]
             pb.close()
+        # an empty shard: rank 0 holds nothing (a batch smaller than the world), rank 1 everything
+        part = emails[:0] if rank == 0 else emails[:50]
+        pb = eng.prepare(EV.from_emails(part), raw=False)
+        ptr, slot, rb = comm.run_allgather(pb)
+        pb.fetch()
+        counts2 = comm.rank_records()
+        ok = ok and counts2 == [0, 50] and slot == 50
+        host = np.zeros((world, slot, rb), dtype=np.uint8)
+        ok = ok and rt.cudaDeviceSynchronize() == 0     # fetch() of an empty batch has nothing to wait for
+        ok = ok and rt.cudaMemcpy(C.c_void_p(host.ctypes.data), C.c_void_p(ptr), C.c_size_t(host.nbytes), 2) == 0
+        ok = ok and not host[0].any() and host[1].any()
+        pb.close()
         q.put((rank, bool(ok), counts))
         comm.close()
         eng.close()
