@@ -137,6 +137,69 @@ def _der(n, e):
     return b"\x30" + ln(len(body)) + body
 
 
+def _is_prime(n):
+    if n < 2 or n % 2 == 0:
+        return n == 2
+    if any(n % q == 0 for q in (3, 5, 7, 11, 13, 17, 19, 23, 29, 31)):
+        return n in (3, 5, 7, 11, 13, 17, 19, 23, 29, 31)
+    d, r = n - 1, 0
+    while d % 2 == 0:
+        d //= 2; r += 1
+    for a in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+        x = pow(a, d, n)
+        if x in (1, n - 1):
+            continue
+        for _ in range(r - 1):
+            x = x * x % n
+            if x == n - 1:
+                break
+        else:
+            return False
+    return True
+
+
+def _prime_from(x, step):
+    x |= 1
+    while not (_is_prime(x) and math.gcd(65537, x - 1) == 1):
+        x += 2 * step
+    return x
+
+
+def test_rsa_kernel_sources_on_moduli_with_long_carry_runs():
+    """Moduli whose limbs are almost all ones or almost all zeros (p, q just below 2^1024; p just above 2^1023 times q just
+    above 2^1024; one factor with a long run of zero limbs): the Montgomery steps then add / propagate across whole lanes,
+    n0inv takes unusual values and the final conditional subtraction sits at its edge.  Valid signatures must verify in the
+    squaring kernel (lanes code 104) and in the plain one, near-misses must not."""
+    forms = [
+        (_prime_from((1 << 1024) - (1 << 20), -1), _prime_from((1 << 1024) - (1 << 40), -1)),      # n = 0xffff...: leading ones
+        (_prime_from((1 << 1023) + (1 << 30), 1), _prime_from((1 << 1024) + (1 << 8), 1)),          # n = 0x8000...0: leading zeros
+        (_prime_from((1 << 1023) + (1 << 700) + 12345, 1), _prime_from((3 << 1022) + (1 << 64), 1)),  # zero limbs in the middle
+    ]
+    for p, q in forms:
+        n = p * q
+        assert n.bit_length() in (2047, 2048)
+        d = pow(65537, -1, (p - 1) * (q - 1))
+        k = (n.bit_length() + 7) // 8
+        der = _der(n, 65537)
+        ks, ds, ss, exp = [], [], [], []
+        for i in range(8):
+            h = hashlib.sha256(b"carry%d" % i).digest()
+            em = b"\x00\x01" + b"\xff" * (k - 54) + b"\x00" + bytes.fromhex("3031300d060960864801650304020105000420") + h
+            s = pow(int.from_bytes(em, "big"), d, n)
+            if i == 5:
+                s ^= 1 << 1500
+            elif i == 6:
+                s = n - 1
+            elif i == 7:
+                s = (n + 1) // 2
+            ks.append(der); ds.append(h); ss.append(s.to_bytes(k, "big"))
+            exp.append(1 if oracle.rsa_verify_sha256(der, h, ss[-1]) == 1 else 0)
+        assert exp[:5] == [1] * 5 and exp[5] == 0
+        assert emu.rsa_verify(ks, ds, ss, 64, 104) == exp, hex(n)[:20]
+        assert emu.rsa_verify(ks, ds, ss, 64, 4) == exp, hex(n)[:20]
+        assert emu.rsa_verify(ks, ds, ss, 64, 8) == exp, hex(n)[:20]
+
+
 @pytest.mark.parametrize("nbits,limbs,lanes,e", [(2047, 64, 8, 65537), (1536, 64, 4, 65537), (2048, 64, 8, 3),
                                                  (1000, 32, 4, 17), (3072, 128, 16, 65537), (4096, 128, 8, 65537)])
 def test_rsa_kernel_source_odd_moduli_and_exponents(nbits, limbs, lanes, e):
