@@ -309,3 +309,39 @@ def test_rsa_kernel_variant_with_dedicated_squaring():
             assert_records_equal(g, e, lab)
     finally:
         eng.close(); ref.close()
+
+
+def test_rsa_kernels_on_moduli_with_long_carry_runs():
+    """The special-form moduli of tests/test_emu_kernels.py (limbs almost all ones / zeros) through the real kernels: the
+    default one (dedicated squaring) and the plain one must both agree with the oracle."""
+    from tests.test_emu_kernels import _der, _prime_from
+    forms = [
+        (_prime_from((1 << 1024) - (1 << 20), -1), _prime_from((1 << 1024) - (1 << 40), -1)),
+        (_prime_from((1 << 1023) + (1 << 30), 1), _prime_from((1 << 1024) + (1 << 8), 1)),
+        (_prime_from((1 << 1023) + (1 << 700) + 12345, 1), _prime_from((3 << 1022) + (1 << 64), 1)),
+    ]
+    ks, ds, ss = [], [], []
+    for p, q in forms:
+        n = p * q
+        d = pow(65537, -1, (p - 1) * (q - 1))
+        k = (n.bit_length() + 7) // 8
+        der = _der(n, 65537)
+        for i in range(40):
+            h = hashlib.sha256(b"carry%d" % i).digest()
+            em = b"\x00\x01" + b"\xff" * (k - 54) + b"\x00" + bytes.fromhex("3031300d060960864801650304020105000420") + h
+            s_ = pow(int.from_bytes(em, "big"), d, n)
+            if i % 8 == 5:
+                s_ ^= 1 << (37 * i % 2000)
+            elif i % 8 == 6:
+                s_ = n - 1
+            elif i % 8 == 7:
+                s_ = (n + 1) // 2
+            ks.append(der); ds.append(h); ss.append(s_.to_bytes(k, "big"))
+    exp = [1 if oracle.rsa_verify_sha256(k, d, s_) == 1 else 0 for k, d, s_ in zip(ks, ds, ss)]
+    assert sum(exp) == 3 * 25
+    eng, ref = z.Engine(now_unix=NOW), z.Engine(flags=z.OPT_NO_SQR, now_unix=NOW)
+    try:
+        assert eng.rsa_verify_batch(ks, ds, ss) == exp
+        assert ref.rsa_verify_batch(ks, ds, ss) == exp
+    finally:
+        eng.close(); ref.close()
