@@ -40,6 +40,29 @@ def test_compiler_oracle_and_kernel_source_agree_with_python_re():
                 assert (int(row[1]), int(row[2])) == want[0], (pat, hay)
 
 
+def test_repetitions_of_sub_expressions_that_can_match_the_empty_string():
+    """Leftmost-first preference in loops whose body can match the empty string depends on the SHAPE of the Thompson NFA,
+    not only on the language.  regex-automata compiles `e+` as one copy of e with a union behind it, and `e*` with such an
+    e as `(e+)?` (rust-lang/regex issue 779: with a plain loop `(|a)*` takes "aaa" where the crate - like Perl - takes
+    the empty string at every position).  csrc/regexc.hpp mirrors those shapes; found by tools/fuzz_regex.py against
+    Python `re`, which agrees with the crate on these patterns."""
+    def spans(pat, hay):
+        d = z.compile_regex(pat)
+        cnt, sp = oracle.dfa_find_iter(d.fwd, d.bwd, hay)
+        return [tuple(x) for x in sp[:cnt]]
+    assert spans(r"(?:|a)*", b"aaa") == [(0, 0), (1, 1), (2, 2), (3, 3)]
+    assert spans(r"(?:|a)+", b"aaa") == [(0, 0), (1, 1), (2, 2), (3, 3)]
+    assert spans(r"(?:a|)+", b"aaa") == [(0, 3)]
+    assert spans(r"1(b?|[xyz]+\d)*", b"01xy9z") == [(1, 2)]            # the empty first alternative ends the loop
+    assert spans(r"1([xyz]+\d|b?)*", b"01xy9z") == [(1, 5)]
+    assert spans(r"b(y*|0??)*", b"xb0bby") == [(1, 2), (3, 4), (4, 6)]
+    assert spans(r"b{1,3}(y*|0??)*", b"xb0bby") == [(1, 2), (3, 6)]
+    assert spans(r"x(?:a??|b)+?y", b"xaby xy") == [(0, 4), (5, 7)]
+    for pat, hay in [(r"1(b?|[xyz]+\d)*", b"01xy9z 1b1 1x0y1"), (r"(\r\n|^)k:( ?[a-z]*)+;", b"k: ab cd;\r\nk:;\r\nk:x y z ;")]:
+        want = [(m.start(), m.end()) for m in re.finditer(pat.encode(), hay) if m.start() != m.end()]
+        assert spans(pat, hay) == want, pat
+
+
 def test_ascii_word_boundaries():
     r"""(?-u:\b) / (?-u:\B) compile (one "previous byte was a word byte" bit per DFA state) and agree with Python's
     bytes-mode \b; Unicode \b is rejected like DFARegex::new rejects it (helpers/src/regex.rs:20 would return Err)."""

@@ -1,0 +1,145 @@
+"""Differential fuzz of the regex compiler (csrc/regexc.hpp through zkb_regex_compile) and the DFA search semantics against
+Python `re` in bytes mode: random patterns from a small grammar (literals, classes, alternation, greedy / lazy / bounded
+repetition, groups, the `(\\r\\n|^)` line prefix zk-email patterns use), random haystacks over a matching alphabet.
+Patterns that can match the empty string are skipped (Rust's and Python's iteration differ there).  CPU only.
+
+    python tools/fuzz_regex.py [seed] [n_patterns]
+"""
+import os
+import random
+import re
+import signal
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import oracle  # noqa: E402  (test infrastructure: the checker)
+import zkemail_rs_b200 as z  # noqa: E402
+
+ALPHA = "abcxyz019 .:@\r\n"
+CLASSES = ["[a-c]", "[^a-c\r\n]", "[0-9]", "[a-z0-9]", r"\d", r"[^\r\n]", "[xyz@.]", "."]
+
+
+def gen_atom(rng, depth):
+    r = rng.random()
+    if r < 0.45:
+        c = rng.choice(ALPHA)
+        return {"\r": "\\r", "\n": "\\n", ".": "\\.", " ": " "}.get(c, c)
+    if r < 0.75:
+        return rng.choice(CLASSES)
+    if depth < 2:
+        return "(" + gen_alt(rng, depth + 1) + ")"
+    return rng.choice(CLASSES)
+
+
+def gen_piece(rng, depth):
+    a = gen_atom(rng, depth)
+    r = rng.random()
+    if r < 0.55:
+        return a
+    q = rng.choice(["+", "*", "?", "{2}", "{1,3}", "{2,}", "+?", "*?", "??", "{1,2}?"])
+    return a + q
+
+
+def gen_concat(rng, depth):
+    return "".join(gen_piece(rng, depth) for _ in range(rng.randint(1, 3)))
+
+
+def gen_alt(rng, depth):
+    return "|".join(gen_concat(rng, depth) for _ in range(1 if rng.random() < 0.7 else rng.randint(2, 3)))
+
+
+def gen_pattern(rng):
+    p = gen_alt(rng, 0)
+    if rng.random() < 0.15:
+        p = r"(\r\n|^)" + p
+    if rng.random() < 0.1:
+        p = "(?i)" + p
+    return p
+
+
+def _alarm(signum, frame):
+    raise TimeoutError
+
+
+def has_nullable_loop(pat):
+    """True if some repetition that may run more than once has a body that can match the empty string.  On those a
+    backtracking engine (an empty iteration ends the loop) and the Thompson construction (closure order) can disagree
+    after a non-empty iteration; DESIGN.md section 5 and tests/golden/regex_pin_extra.json."""
+    try:
+        import re._parser as sp        # Python >= 3.11
+    except ImportError:                 # pragma: no cover
+        import sre_parse as sp
+
+    def walk(items):
+        for op, av in items:
+            name = str(op)
+            if name in ("MAX_REPEAT", "MIN_REPEAT", "POSSESSIVE_REPEAT"):
+                lo, hi, body = av
+                if hi > 1 and body.getwidth()[0] == 0:
+                    return True
+                if walk(body):
+                    return True
+            elif name == "SUBPATTERN":
+                if walk(av[3]):
+                    return True
+            elif name == "BRANCH":
+                if any(walk(b) for b in av[1]):
+                    return True
+        return False
+    return walk(sp.parse(pat))
+
+
+def main():
+    signal.signal(signal.SIGALRM, _alarm)
+    seed = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
+    rng = random.Random(seed)
+    tested = skipped = bad = nullable = 0
+    for _ in range(n):
+        pat = gen_pattern(rng)
+        try:
+            py = re.compile(pat.encode())
+        except re.error:
+            skipped += 1
+            continue
+        if py.match(b"") or py.search(b"") is not None:
+            skipped += 1            # can match the empty string
+            continue
+        try:
+            d = z.compile_regex(pat)
+        except Exception as ex:   # noqa: BLE001
+            if "too large" in str(ex):
+                skipped += 1        # the compiler's state limit, a documented refusal
+                continue
+            print("COMPILE FAILED", repr(pat), ex, file=sys.stderr)
+            bad += 1
+            continue
+        tested += 1
+        for _h in range(12):
+            hay = "".join(rng.choice(ALPHA) for _ in range(rng.randint(0, 60))).encode()
+            try:                     # Python's backtracking matcher can take exponential time on nested repetitions
+                signal.alarm(2)
+                ms = list(py.finditer(hay))
+                signal.alarm(0)
+            except TimeoutError:
+                break
+            if any(m.start() == m.end() for m in ms):
+                continue            # an empty match somewhere: iteration rules differ
+            want = [(m.start(), m.end()) for m in ms]
+            cnt, spans = oracle.dfa_find_iter(d.fwd, d.bwd, hay)
+            got = [tuple(s) for s in spans[:cnt]]
+            if cnt != len(want) or got != want[:len(got)]:
+                if has_nullable_loop(pat):
+                    nullable += 1   # the one class where the two families of engines differ by construction
+                    break
+                bad += 1
+                if bad < 8:
+                    print("MISMATCH", repr(pat), hay, "python", want, "dfa", cnt, got, file=sys.stderr)
+                break
+    print(f"fuzz_regex seed {seed}: {tested} patterns tested, {skipped} skipped, mismatches {bad}, "
+          f"disagreements inside loops with a nullable body {nullable}")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -6,7 +6,7 @@
 //!   emails_v1.json, rfc_vectors.json  -> zkemail_core::verify_email (core/src/circuits.rs:9-29; a panic is recorded with
 //!                                        its message), cfdkim::canonicalize_signed_email (core/src/circuits.rs:34-35),
 //!                                        VerificationOutput::abi_encode (core/src/io.rs:27-53)
-//!   regex_v1.json                     -> dfa::regex::Regex::new + to_bytes_little_endian exactly as
+//!   regex_v1.json (+ regex_pin_extra.json) -> dfa::regex::Regex::new + to_bytes_little_endian exactly as
 //!                                        helpers/src/regex.rs:7-14 (create_dfa) and find_iter spans (core/src/regex.rs:36)
 use base64::{engine::general_purpose::STANDARD as B64, Engine};
 use regex_automata::dfa::regex::Regex as DFARegex;
@@ -98,7 +98,13 @@ fn main() {
     }
     // regex_v1.json: [{pattern, haystack, spans}] -> group the haystacks by pattern
     let mut by_pattern: Vec<(String, Vec<Vec<u8>>)> = vec![];
-    for g in read("regex_v1.json").as_array().unwrap() {
+    // regex_pin_extra.json: [{pattern, haystack}] without expected spans - patterns on which backtracking engines and the
+    // Thompson construction may disagree (loops whose body can match the empty string); the crate's answer is the pin
+    let mut groups: Vec<Value> = read("regex_v1.json").as_array().unwrap().clone();
+    if std::path::Path::new(&format!("{dir}/regex_pin_extra.json")).exists() {
+        groups.extend(read("regex_pin_extra.json").as_array().unwrap().iter().cloned());
+    }
+    for g in groups.iter() {
         let p = g["pattern"].as_str().unwrap().to_string();
         let h = b64(&g["haystack"]);
         match by_pattern.iter_mut().find(|(q, _)| *q == p) {

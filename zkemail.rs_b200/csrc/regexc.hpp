@@ -665,6 +665,19 @@ struct NfaBuilder {
   bool reverse;
   NfaBuilder(const std::vector<Node>& nd, Nfa& n, bool rev) : nodes(nd), nfa(n), reverse(rev) {}
 
+  // shortest match length in bytes, saturated (regex-syntax: Properties::minimum_len; only "is it zero" matters here)
+  uint32_t min_len(int id) const {
+    const Node& nd = nodes[id];
+    switch (nd.kind) {
+      case Node::EMPTY: case Node::LOOK: return 0;
+      case Node::CLASS: return 1;
+      case Node::CONCAT: { uint64_t a = 0; for (int k : nd.kids) a += min_len(k); return a > 0x7fffffffu ? 0x7fffffffu : (uint32_t)a; }
+      case Node::ALT: { uint32_t m = 0x7fffffffu; for (int k : nd.kids) m = std::min(m, min_len(k)); return nd.kids.empty() ? 0 : m; }
+      case Node::REPEAT: { uint64_t a = (uint64_t)nd.min * min_len(nd.kids[0]); return a > 0x7fffffffu ? 0x7fffffffu : (uint32_t)a; }
+    }
+    return 0;
+  }
+
   int compile(int id, int next) {
     if (nfa.overflow) return next;
     const Node& nd = nodes[id];
@@ -708,20 +721,36 @@ struct NfaBuilder {
         return nfa.uni(alts);
       }
       case Node::REPEAT: {
+        // The shapes of regex-automata's Thompson compiler (c_at_least / c_bounded / c_exactly), not just the language:
+        // leftmost-first preference is decided by the order in which the epsilon closure meets the states, and that
+        // depends on how many copies of the sub-expression exist and where the back edge goes.
+        //   e{n,}, n >= 1 : e^(n-1) then ONE copy of e with a union behind it (back to that copy | exit)
+        //   e*, e cannot match the empty string : union(e -> union | exit)
+        //   e*, e can match the empty string    : (e+)?  - with the plain loop the empty path through e would come back
+        //        to the loop head, be dropped as already visited, and e's other alternatives would outrank the exit,
+        //        so that (|a)* on "aa" took "aa" where the crate (and Perl) take "" (rust-lang/regex issue 779)
+        //   e{m,n} : e^m then nested optionals e(e(e)?)?
         int sub = nd.kids[0];
         int t = next;
+        uint32_t copies = nd.min;
         if (nd.max == INF) {
-          int loop = nfa.uni({});
-          int body = compile(sub, loop);
-          if (nd.greedy) nfa.st[loop].alts = {body, next}; else nfa.st[loop].alts = {next, body};
-          t = loop;
+          int u = nfa.uni({});
+          int body = compile(sub, u);
+          if (nd.greedy) nfa.st[u].alts = {body, next}; else nfa.st[u].alts = {next, body};
+          if (nd.min == 0) {
+            if (min_len(sub) > 0) t = u;
+            else t = nd.greedy ? nfa.uni({body, next}) : nfa.uni({next, body});
+          } else {
+            t = body;          // the copy in front of the union is the last of the n mandatory ones
+            copies = nd.min - 1;
+          }
         } else {
           for (uint32_t i = nd.min; i < nd.max; i++) {
             int body = compile(sub, t);
             t = nd.greedy ? nfa.uni({body, next}) : nfa.uni({next, body});
           }
         }
-        for (uint32_t i = 0; i < nd.min; i++) t = compile(sub, t);
+        for (uint32_t i = 0; i < copies; i++) t = compile(sub, t);
         return t;
       }
     }
