@@ -448,7 +448,8 @@ struct Parser {
         pos++;
         if (mx != INF && mx < mn) { fail("invalid repetition range"); return -1; }
       } else break;
-      if (nodes[atom].kind == Node::LOOK) { fail("repetition operator missing expression"); return -1; }
+      // (a repetition of an assertion - `^*`, `(\b)+` - is legal in regex-syntax: only an empty expression or a flag
+      // group in front of the operator is "repetition operator missing expression")
       bool greedy = true;
       if (pos < n && p[pos] == '?') { greedy = false; pos++; }
       if (f.U) greedy = !greedy;
