@@ -3,7 +3,10 @@ Python `re` in bytes mode: random patterns from a small grammar (literals, class
 repetition, groups, the `(\\r\\n|^)` line prefix zk-email patterns use), random haystacks over a matching alphabet.
 Patterns that can match the empty string are skipped (Rust's and Python's iteration differ there).  CPU only.
 
-    python tools/fuzz_regex.py [seed] [n_patterns]
+    python tools/fuzz_regex.py [seed] [n_patterns] [--emu]
+
+--emu also runs the DFA scan KERNEL SOURCE (csrc/dfa.cuh under host emulation, tests/emu) over every haystack and holds its
+match count and first span to the oracle's: random tables with anchors, look-behind start states and word boundaries.
 """
 import os
 import random
@@ -101,8 +104,13 @@ def has_nullable_loop(pat):
 
 def main():
     signal.signal(signal.SIGALRM, _alarm)
-    seed = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-    n = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    with_emu = "--emu" in sys.argv
+    if with_emu:
+        from tests import emu
+    seed = int(args[0]) if len(args) > 0 else 1
+    n = int(args[1]) if len(args) > 1 else 2000
+    kernel_bad = 0
     rng = random.Random(seed)
     tested = skipped = bad = nullable = 0
     for _ in range(n):
@@ -112,8 +120,9 @@ def main():
         except re.error:
             skipped += 1
             continue
-        if py.match(b"") or py.search(b"") is not None:
-            skipped += 1            # can match the empty string
+        nullable_pattern = py.search(b"") is not None     # can match the empty string: no comparison with Python
+        if nullable_pattern and not with_emu:
+            skipped += 1
             continue
         try:
             d = z.compile_regex(pat)
@@ -125,6 +134,19 @@ def main():
             bad += 1
             continue
         tested += 1
+        if with_emu:
+            hays = ["".join(rng.choice(ALPHA) for _ in range(rng.randint(0, 80))).encode() for _ in range(16)]
+            rows = emu.dfa_scan(d.fwd, d.bwd, hays)
+            for hay, row in zip(hays, rows):
+                cnt, spans = oracle.dfa_find_iter(d.fwd, d.bwd, hay)
+                first = tuple(spans[0]) if cnt else (0, 0)
+                if int(row[0]) != cnt or (cnt and (int(row[1]), int(row[2])) != first):
+                    kernel_bad += 1
+                    if kernel_bad < 6:
+                        print("KERNEL MISMATCH", repr(pat), hay, "oracle", cnt, first, "kernel", [int(x) for x in row], file=sys.stderr)
+        if nullable_pattern:
+            skipped += 1            # (the kernel source was still held to the oracle above)
+            continue
         for _h in range(12):
             hay = "".join(rng.choice(ALPHA) for _ in range(rng.randint(0, 60))).encode()
             try:                     # Python's backtracking matcher can take exponential time on nested repetitions
@@ -149,8 +171,8 @@ def main():
                     print("MISMATCH", repr(pat), hay, "python", want, "dfa", cnt, got, file=sys.stderr)
                 break
     print(f"fuzz_regex seed {seed}: {tested} patterns tested, {skipped} skipped, mismatches {bad}, "
-          f"disagreements inside loops with a nullable body {nullable}")
-    return 1 if bad else 0
+          f"disagreements inside loops with a nullable body {nullable}" + (f", kernel-source mismatches {kernel_bad}" if with_emu else ""))
+    return 1 if bad or kernel_bad else 0
 
 
 if __name__ == "__main__":
