@@ -67,6 +67,8 @@ def gen_pattern(rng):
         p, q = r"(\r\n|^)" + p, r"(\r\n|^)" + q
     if rng.random() < 0.1:
         p, q = "(?i)" + p, "(?i)" + q
+    if rng.random() < 0.1:
+        p, q = "(?s)" + p, "(?s)" + q
     return p, q
 
 
