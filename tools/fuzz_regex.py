@@ -3,10 +3,11 @@ Python `re` in bytes mode: random patterns from a small grammar (literals, class
 repetition, groups, the `(\\r\\n|^)` line prefix zk-email patterns use), random haystacks over a matching alphabet.
 Patterns that can match the empty string are skipped (Rust's and Python's iteration differ there).  CPU only.
 
-    python tools/fuzz_regex.py [seed] [n_patterns] [--emu]
+    python tools/fuzz_regex.py [seed] [n_patterns] [--emu | --gpu]
 
 --emu also runs the DFA scan KERNEL SOURCE (csrc/dfa.cuh under host emulation, tests/emu) over every haystack and holds its
 match count and first span to the oracle's: random tables with anchors, look-behind start states and word boundaries.
+--gpu does the same with the real kernel through zkb_dfa_scan_batch (needs a B200), with and without soft-break removal.
 """
 import os
 import random
@@ -107,8 +108,16 @@ def has_nullable_loop(pat):
 def main():
     signal.signal(signal.SIGALRM, _alarm)
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
-    with_emu = "--emu" in sys.argv
-    if with_emu:
+    with_gpu = "--gpu" in sys.argv
+    with_emu = "--emu" in sys.argv or with_gpu
+    if with_gpu:
+        eng = z.Engine()
+
+        class emu:    # same call shape as tests.emu
+            @staticmethod
+            def dfa_scan(fwd, bwd, hays, qp=False):
+                return eng.dfa_scan_batch(z.DFA(fwd, bwd), hays, qp=qp)
+    elif with_emu:
         from tests import emu
     seed = int(args[0]) if len(args) > 0 else 1
     n = int(args[1]) if len(args) > 1 else 2000
@@ -138,7 +147,12 @@ def main():
         tested += 1
         if with_emu:
             hays = ["".join(rng.choice(ALPHA) for _ in range(rng.randint(0, 80))).encode() for _ in range(16)]
-            rows = emu.dfa_scan(d.fwd, d.bwd, hays)
+            if with_gpu and rng.random() < 0.3:       # quoted-printable soft breaks removed on the fly (core/src/email.rs:61-86)
+                hays = [h.replace(b"y", b"=\r\n") for h in hays]
+                rows = emu.dfa_scan(d.fwd, d.bwd, hays, qp=True)
+                hays = [oracle.qp_clean(h)[0] for h in hays]
+            else:
+                rows = emu.dfa_scan(d.fwd, d.bwd, hays)
             for hay, row in zip(hays, rows):
                 cnt, spans = oracle.dfa_find_iter(d.fwd, d.bwd, hay)
                 first = tuple(spans[0]) if cnt else (0, 0)
