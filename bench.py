@@ -548,6 +548,12 @@ def main():
                        "rsa_lanes": args.rsa_lanes or 4},
             "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_int": roofline_int, "cpu_baseline": cpu_baseline,
             "e2e": e2e, "e2e_registered": e2e_registered, "value_from_raw": value_from_raw, "with_regex": with_regex,
+            # what bounds the end-to-end numbers as ranks are added on ONE box: the kernels need ~35 ms of
+            # stream time per 1 M emails and rank, everything else is the host side the ranks share
+            "e2e_scaling": {"ranks": world, "host_threads_per_rank": threads,
+                            "e2e_bound": "host copy of every raw message into pinned staging (pageable callers; the box's host threads are split between the ranks)",
+                            "e2e_registered_bound": "PCIe Gen5 x16 per GPU (~52 GB/s = ~10 M emails/s of 5.2 KB messages) until the box's host-memory bandwidth is shared by the links",
+                            "kernel_stream_ms_per_step": (value_from_raw or {}).get("ms_per_step")},
             "gpu_launches": stats["kernel_launches"] * K,
             "kernel_ms": fam_best, "clocks": clocks.summary(), "int_pipe_peaks": peaks, "nproc": ncpu,
         }
