@@ -362,7 +362,8 @@ struct zkb_engine {
   std::atomic<int> live_batches{0};   // resident batches hold key ids: the table is not trimmed while any is alive
   cudaEvent_t ev[10] = {nullptr};
   cudaStream_t aux_stream = nullptr;          // zkb_batch_run_async: hashing of the next chunk beside the RSA of this one
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t aux_stream2 = nullptr;         // raw-resident batches: chunks alternate between the two side streams
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
   std::vector<cudaEvent_t> ev_pre;            // one per resident chunk index: "pre phase of chunk k done"
   uint64_t last_h2d = 0, last_d2h = 0, last_fallback = 0;   // of the last zkb_verify_batch
   // ZKB_PROFILE accounting of the call in progress (calls on one engine are serialised by run_mu)
@@ -1586,6 +1587,8 @@ int zkb_engine_create(const zkb_options* opt, zkb_engine** out) {
     int lo = 0, hi = 0;
     CKE(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CKE(cudaStreamCreateWithPriority(&e->aux_stream, cudaStreamNonBlocking, hi));
+    CKE(cudaStreamCreateWithPriority(&e->aux_stream2, cudaStreamNonBlocking, hi));
+    CKE(cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming));
     CKE(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CKE(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   }
@@ -1611,7 +1614,9 @@ void zkb_engine_destroy(zkb_engine* e) {
   for (auto& ev : e->ev_pre) if (ev) cudaEventDestroy(ev);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->ev_join2) cudaEventDestroy(e->ev_join2);
   if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
+  if (e->aux_stream2) cudaStreamDestroy(e->aux_stream2);
   if (e->d_keytab) cudaFree(e->d_keytab);
   if (e->borrowed_registrations == 0)   // engines of a zkb_multi other than the first only borrow the first one's registrations
     for (auto& r : e->registered) cudaHostUnregister(const_cast<uint8_t*>(r.first));
@@ -1966,16 +1971,22 @@ static int batch_run_async_locked(zkb_batch* b, const AfterChunk* after_chunk) {
   // 4 KB mail (measured: +0.5 %, and capping the RSA CTAs per SM to make room for hashing CTAs, or keeping the SHA
   // additions off the FMA pipe, only lost time): IMAD.WIDE holds the issue port, the SM is saturated by either kernel.
   // The side stream forks from / joins the engine stream, so callers still order against that one stream.
-  cudaStream_t aux = e->aux_stream;
+  // Raw-resident batches (front end + canonicalisation in every run) alternate the chunks between TWO side streams: the
+  // latency-bound canonicalisation and the issue-bound front end of chunk k + 1 then run beside the ALU-bound hashing of
+  // chunk k instead of behind it (chunks share nothing but read-only tables).
+  cudaStream_t auxs[2] = {e->aux_stream, (b->raw && e->aux_stream2 && !e->has(ZKB_OPT_NO_OVERLAP)) ? e->aux_stream2 : e->aux_stream};
+  const bool two = auxs[1] != auxs[0];
   while (e->ev_pre.size() < nc) {
     cudaEvent_t ev = nullptr;
     CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     e->ev_pre.push_back(ev);
   }
   CK(cudaEventRecord(e->ev_fork, s));
-  CK(cudaStreamWaitEvent(aux, e->ev_fork, 0));
+  CK(cudaStreamWaitEvent(auxs[0], e->ev_fork, 0));
+  if (two) CK(cudaStreamWaitEvent(auxs[1], e->ev_fork, 0));
   for (size_t k = 0; k < nc; k++) {
     DeviceChunk* d = b->dev[k];
+    cudaStream_t aux = auxs[k & 1];
     size_t o_flags, o_dfa;
     out_layout(d->M, d->C, d->NE, d->P, o_flags, o_dfa);
     CK(cudaMemsetAsync(d->out.p + o_flags, 0, align_up((size_t)d->C * 4, 16), aux));
@@ -1987,8 +1998,12 @@ static int batch_run_async_locked(zkb_batch* b, const AfterChunk* after_chunk) {
     if (rc) return rc;
     if (after_chunk && (rc = (*after_chunk)(k, s)) != 0) return rc;
   }
-  CK(cudaEventRecord(e->ev_join, aux));
+  CK(cudaEventRecord(e->ev_join, auxs[0]));
   CK(cudaStreamWaitEvent(s, e->ev_join, 0));
+  if (two) {
+    CK(cudaEventRecord(e->ev_join2, auxs[1]));
+    CK(cudaStreamWaitEvent(s, e->ev_join2, 0));
+  }
   b->ran = true;
   return ZKB_OK;
 }
